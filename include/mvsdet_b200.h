@@ -1,0 +1,201 @@
+/*
+ * mvsdet_b200 -- C ABI of the B200-native MVSDet hot path.
+ *
+ * The reference (Pixie8888/MVSDet) has NO native/FFI boundary on this path: the
+ * plane sweep, depth top-k and voxel back-projection are plain PyTorch calls
+ * inlined in MVSDet.extract_feat (projects/NeRF-Det/nerfdet/mvsdet.py:430-515).
+ * The boundary below is therefore the one a maintainer would bind from that
+ * Python code (ctypes stub in INTEGRATION.md); every entry point names the
+ * reference lines whose work it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain C, no torch / CUDA types in the signatures; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching
+ *     allocator); the library never allocates, frees or synchronises, so every
+ *     call is re-entrant and capturable in a CUDA graph;
+ *   - return value: MVSD_OK (0) or a non-zero mvsd_status; nothing is thrown
+ *     across the ABI.  mvsd_last_error() gives a human-readable message for the
+ *     calling thread's last failure;
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point returns MVSD_ERR_CUDA.
+ *
+ * Layouts.  "nhwc" feature maps are [V][H][W][C] with C fastest, i.e. a
+ * torch tensor of logical shape [V,C,H,W] in torch.channels_last memory
+ * format.  Volumes with layout MVSD_CHANNELS_LAST are [V][D][H][W][C]
+ * (torch.channels_last_3d of logical [V,C,D,H,W]).  C must be a multiple of 4
+ * and at most 512.  Accumulation is always fp32.
+ */
+#ifndef MVSDET_B200_H_
+#define MVSDET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVSD_ABI_VERSION 1
+
+typedef enum {
+  MVSD_OK = 0,
+  MVSD_ERR_INVALID_ARG = 1,   /* null pointer, non-positive dim, bad enum      */
+  MVSD_ERR_UNSUPPORTED = 2,   /* legal request outside the compiled envelope  */
+  MVSD_ERR_CUDA = 3           /* launch / device error (no device, bad ptr..) */
+} mvsd_status;
+
+typedef enum { MVSD_F32 = 0, MVSD_BF16 = 1 } mvsd_dtype;
+typedef enum { MVSD_CHANNELS_LAST = 0, MVSD_CHANNELS_FIRST = 1 } mvsd_layout;
+typedef enum {
+  MVSD_BP_MEAN = 0,      /* sum over views / (count + 1e-8), 0 where count==0 */
+  MVSD_BP_SUM = 1,       /* partial sums + counts (view-sharded multi-GPU)    */
+  MVSD_BP_PER_VIEW = 2   /* un-aggregated per-view volume (reference API)     */
+} mvsd_bp_mode;
+
+/* ---- library info ------------------------------------------------------ */
+int mvsd_abi_version(void);
+const char* mvsd_build_info(void);          /* "sm_100a, nvcc 12.9, ..."     */
+const char* mvsd_status_string(int status);
+const char* mvsd_last_error(void);          /* thread-local, never NULL      */
+/* Tuning knobs for experiments (variant selection); returns previous value,
+ * or -1 for an unknown key.  Keys: 0 = plane-sweep forward pixels per warp
+ * (1,2,4), 1 = plane-sweep patch width in pixels, 2 = plane-sweep backward
+ * pixels per warp (1,2).  0 = library default.                               */
+int mvsd_set_tuning(int key, int value);
+/* Number of kernel launches issued through this library by the calling
+ * process since load (bench.py's gpu_launches counter).                      */
+int64_t mvsd_launch_count(void);
+
+/* ---- layout helpers ----------------------------------------------------- */
+/* [V,C,H,W] fp32 contiguous (what the reference's FPN emits, mvsdet.py:373-376)
+ * -> nhwc of dst_dtype. */
+int mvsd_pack_nchw_to_nhwc(const float* src, void* dst, int dst_dtype,
+                           int V, int C, int H, int W, void* stream);
+/* nhwc fp32 -> [V,C,H,W] fp32; accumulate != 0 adds into dst. */
+int mvsd_unpack_nhwc_to_nchw(const float* src, float* dst, int accumulate,
+                             int V, int C, int H, int W, void* stream);
+
+/* ---- a3+a4: fused plane-sweep variance ---------------------------------- *
+ * Replaces mvsdet.py:439-467 (ref_volume repeat, k x homo_warping
+ * [mvs_models/module.py:105-146], sum / square-sum, variance).
+ *   feat     nhwc [V,H,W,C] of feat_dtype
+ *   nbr_ids  [V,k] int32, neighbour view of each reference view (mvsdet.py:432-434)
+ *   hom      [V,k,12] fp32: rows of rot (9) then trans (3) of
+ *            P_nbr @ inverse(P_ref) (module.py:116-118)
+ *   depth_values [V,D] fp32 (mvsdet.py:450)
+ *   out      variance, [V,D,H,W,C] (MVSD_CHANNELS_LAST) of out_dtype
+ * k may be 0..4 (k=0: a single view, variance is exactly 0).
+ * View sharding: V counts the REFERENCE views of this call; reference view v
+ * reads feat[ref_begin + v] while nbr_ids index feat directly, so a rank can
+ * sweep a slice [ref_begin, ref_begin+V) of a scene whose feature maps are all
+ * resident (ref_begin = 0 for a whole scene).                                */
+int mvsd_plane_sweep_fwd(const void* feat, int feat_dtype,
+                         const int32_t* nbr_ids, const float* hom,
+                         const float* depth_values,
+                         void* out, int out_dtype, int out_layout,
+                         int V, int C, int D, int H, int W, int k, int ref_begin,
+                         void* stream);
+/* Backward of the above (what autograd computes through mvsdet.py:439-467):
+ *   g_out   dL/dvariance, same layout as `out`, of g_dtype
+ *   g_feat  nhwc fp32, same extent as feat; contributions are ADDED (caller
+ *           zero-fills). */
+int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout,
+                         const void* feat, int feat_dtype,
+                         const int32_t* nbr_ids, const float* hom,
+                         const float* depth_values, float* g_feat,
+                         int V, int C, int D, int H, int W, int k, int ref_begin,
+                         void* stream);
+
+/* ---- a3 alone: homo_warping (mvs_models/module.py:105-146) --------------- *
+ *   src  nhwc [B,H,W,C]; hom [B,12]; depth_values [B,D]; out [B,D,H,W,C].   */
+int mvsd_homo_warp_fwd(const void* src, int src_dtype, const float* hom,
+                       const float* depth_values, void* out, int out_dtype,
+                       int out_layout, int B, int C, int D, int H, int W,
+                       void* stream);
+int mvsd_homo_warp_bwd(const void* g_out, int g_dtype, int g_layout,
+                       const float* hom, const float* depth_values,
+                       float* g_src, int B, int C, int D, int H, int W,
+                       void* stream);
+
+/* ---- a5-a7: softmax / sigmoid / top-k / depth expectation ---------------- *
+ * Replaces mvsdet.py:470-482, sample_depth_prob (:266-283) and
+ * compute_avg_depth (:298-317).
+ *   cost_out  the cost-regularisation output, logical [V,2,D,H,W]; element
+ *             strides s_v, s_c, s_d, s_p (pixel) let it be NCDHW-contiguous
+ *             (s_c=D*H*W, s_d=H*W, s_p=1) or channels_last_3d (s_c=1,
+ *             s_d=2*H*W, s_p=2)
+ *   prob_volume, off_pred  [V,D,H,W] fp32 (either may be NULL)
+ *   est_depth, est_dens    [V,T,H,W] fp32;  est_idx [V,T,H,W] int64
+ *   depth_coding           [V,H,W] fp32 (may be NULL)
+ * Top-k order: descending probability, ties -> lowest plane index first.
+ * raw != 0: channel 0 of cost_out already holds probabilities and channel 1
+ * offsets in [0,1] (the stand-alone sample_depth_prob / compute_avg_depth API);
+ * softmax / sigmoid are skipped, forward and backward.                        */
+int mvsd_depth_topk_fwd(const float* cost_out, int64_t s_v, int64_t s_c,
+                        int64_t s_d, int64_t s_p,
+                        float* prob_volume, float* off_pred, float* est_depth,
+                        float* est_dens, int64_t* est_idx, float* depth_coding,
+                        float near, float interval, int raw,
+                        int V, int D, int H, int W, int T, void* stream);
+/* Backward: any of the four upstream gradients may be NULL (treated as 0).
+ *   g_cost_out  [V,2,D,H,W] fp32 contiguous, fully overwritten.              */
+int mvsd_depth_topk_bwd(const float* cost_out, int64_t s_v, int64_t s_c,
+                        int64_t s_d, int64_t s_p, const int64_t* est_idx,
+                        const float* g_prob_volume, const float* g_off_pred,
+                        const float* g_est_depth, const float* g_est_dens,
+                        const float* g_depth_coding, float* g_cost_out,
+                        float near, float interval, int raw,
+                        int V, int D, int H, int W, int T, void* stream);
+
+/* ---- a10+a11: probabilistic voxel back-projection ------------------------ *
+ * Replaces backproject_Weigh (mvsdet.py:1372-1492) and the view aggregation
+ * (mvsdet.py:511-515, :681-682).
+ *   feat        nhwc [V,feat_h,feat_w,C] of feat_dtype; only rows < h and
+ *               columns < w are addressed (the reference crops, mvsdet.py:499)
+ *   points      [3,N] fp32 voxel centres (get_points, mvsdet.py:1316-1327)
+ *   projection  [V,3,4] fp32 (_compute_projection, mvsdet.py:1124-1156)
+ *   depth, prob hypotheses of logical shape [V,h,w,T] addressed with element
+ *               strides dp_sv, dp_sy, dp_sx, dp_st (same strides for both)
+ *   vs_z        voxel_size[2] (depth-test half width, mvsdet.py:1407-1408)
+ *   mode        mvsd_bp_mode
+ *   out         MEAN/SUM: [N,C] (MVSD_CHANNELS_LAST) or [C,N] (CHANNELS_FIRST)
+ *               PER_VIEW: [V,N,C], caller zero-fills
+ *   count       [N] int32, number of valid views per voxel (MEAN/SUM; may be
+ *               NULL in PER_VIEW)
+ *   valid       [V,N] uint8 per-view mask (may be NULL)
+ *   weight      [V,N] fp32 per-view weight (may be NULL)                      */
+int mvsd_backproject_fwd(const void* feat, int feat_dtype, int feat_h, int feat_w,
+                         const float* points, const float* projection,
+                         const float* depth, const float* prob,
+                         int64_t dp_sv, int64_t dp_sy, int64_t dp_sx, int64_t dp_st,
+                         float vs_z, int mode, float* out, int out_layout,
+                         int32_t* count, uint8_t* valid, float* weight,
+                         int V, int C, int h, int w, int T, int N, void* stream);
+/* Backward.
+ *   g_out   MEAN/SUM: dL/dout, same layout as out; PER_VIEW: [V,N,C]
+ *   count   MEAN: the forward's count (s_u = 1/(count+1e-8)); else NULL
+ *   g_feat  nhwc fp32 [V,feat_h,feat_w,C], ADDED into
+ *   g_pn    dL/d(normalised hypothesis probability), same strides as prob,
+ *           ADDED into (caller zero-fills); feed to mvsd_prob_norm_bwd.       */
+int mvsd_backproject_bwd(const float* g_out, int g_layout, int mode,
+                         const int32_t* count,
+                         const void* feat, int feat_dtype, int feat_h, int feat_w,
+                         const float* points, const float* projection,
+                         const float* depth, const float* prob,
+                         int64_t dp_sv, int64_t dp_sy, int64_t dp_sx, int64_t dp_st,
+                         float vs_z, float* g_feat, float* g_pn,
+                         int V, int C, int h, int w, int T, int N, void* stream);
+/* pn = prob / sum_T prob (mvsdet.py:1395-1396) backward: g_pn -> g_prob, all
+ * three addressed with the dp_* strides; overwrites g_prob on the [h,w] crop. */
+int mvsd_prob_norm_bwd(const float* prob, const float* g_pn, float* g_prob,
+                       int64_t dp_sv, int64_t dp_sy, int64_t dp_sx, int64_t dp_st,
+                       int V, int h, int w, int T, void* stream);
+/* After an all-reduce of SUM partials: out = count ? sum/(count+1e-8) : 0.
+ * In place is allowed (out == sum).                                           */
+int mvsd_voxel_normalize(const float* sum, const int32_t* count, float* out,
+                         int layout, int C, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* MVSDET_B200_H_ */

@@ -1,0 +1,98 @@
+"""Drop-in mirrors of the reference's hot-path functions.
+
+Same names, argument meaning, return shapes and error behaviour as
+  homo_warping            projects/NeRF-Det/nerfdet/mvs_models/module.py:105-146
+  sample_depth_prob       MVSDet.sample_depth_prob, mvsdet.py:266-283
+  compute_avg_depth       MVSDet.compute_avg_depth, mvsdet.py:298-317
+  backproject_Weigh       mvsdet.py:1372-1492
+  get_points, knn, get_nearest_pose_ids, collect_proj, _compute_projection
+but every tensor op runs in the sm_100a kernels of this package (ops.py).  The
+methods of the reference that read ``self`` take the same values as keyword
+arguments (``near``, ``depth_interval``).  The fused entry points the
+replacement of mvsdet.py:430-515 actually uses are in ``hotpath.py``.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from . import geometry as G
+from . import ops
+
+knn = G.knn
+get_nearest_pose_ids = G.get_nearest_pose_ids
+collect_proj = G.collect_proj
+get_points = G.get_points
+_compute_projection = G.compute_projection
+
+__all__ = ["homo_warping", "sample_depth_prob", "compute_avg_depth", "backproject_Weigh",
+           "knn", "get_nearest_pose_ids", "collect_proj", "get_points",
+           "_compute_projection"]
+
+
+def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.Tensor,
+                 depth_values: torch.Tensor) -> torch.Tensor:
+    """src_fea [B,C,H,W], src_proj/ref_proj [B,4,4], depth_values [B,D]
+    -> warped [B,C,D,H,W] (channels_last_3d memory).  No gradient reaches the
+    projection matrices or the depths (the reference builds the grid under
+    no_grad, module.py:115)."""
+    if depth_values.dim() != 2:
+        raise ValueError("per-pixel depth_values [B,D,H,W] (module.py:130-133) is not used by "
+                         "MVSDet and not implemented")
+    with torch.no_grad():
+        hom = G.homography_params(src_proj.float(), ref_proj.float()).to(src_fea.device)
+    feat = ops.pack_features(src_fea, src_fea.dtype if src_fea.dtype == torch.bfloat16 else torch.float32)
+    return ops.homo_warp(feat, hom, depth_values.to(src_fea.device).float(),
+                         out_dtype=torch.float32)
+
+
+def _stack_prob_off(prob_volume, off_pred):
+    if prob_volume.shape != off_pred.shape or prob_volume.dim() != 4:
+        raise ValueError("prob_volume and off_pred must both be [V,D,H,W]")
+    return torch.stack((prob_volume, off_pred), dim=1)
+
+
+def sample_depth_prob(prob_volume: torch.Tensor, off_pred: torch.Tensor, topk: int = 3, *,
+                      near: float, depth_interval: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """prob_volume, off_pred [V,D,H,W] (already softmax-ed / sigmoid-ed) ->
+    (est_depth, est_density) each [V,topk,H,W]."""
+    res = ops.topk_hypotheses(_stack_prob_off(prob_volume, off_pred), near, depth_interval, topk)
+    return res[0], res[1]
+
+
+def compute_avg_depth(prob_volume: torch.Tensor, off_pred: torch.Tensor, *, near: float,
+                      depth_interval: float) -> torch.Tensor:
+    """Depth expectation [V,H,W] = sum_d p_d (d*interval + near + off_d*interval)."""
+    res = ops.topk_hypotheses(_stack_prob_off(prob_volume, off_pred), near, depth_interval, 1)
+    return res[3]
+
+
+def backproject_Weigh(features, points, projection, depth, voxel_size, prob, gt_depth=None,
+                      save_dir=None, img_meta=None, depth_mean=None):
+    """features [V,C,h,w] (may be a crop of a larger map), points [3,nx,ny,nz],
+    projection [V,3,4], depth/prob [V,h*w,num_surface,T]
+    -> (volume [V,C,nx,ny,nz], valid bool [V,1,nx,ny,nz], gap_all, rmse).
+
+    ``gt_depth`` only feeds debug scalars in the reference (mvsdet.py:1431-1486);
+    that branch is not part of the path: passing it raises."""
+    if gt_depth is not None:
+        raise ValueError("the gt_depth debug branch of backproject_Weigh (mvsdet.py:1431-1486) "
+                         "is outside the accelerated path")
+    v, c, h, w = features.shape
+    nx, ny, nz = points.shape[-3:]
+    dtype = features.dtype if features.dtype == torch.bfloat16 else torch.float32
+    s0, s1, s2, s3 = features.stride()
+    if (features.dtype == dtype and s1 == 1 and s3 == c and s2 % c == 0 and s2 >= w * c
+            and s0 % s2 == 0 and s0 >= h * s2):
+        # a top-left crop of a channels-last map (mvsdet.py:499): address the
+        # parent map in place, the kernel only touches rows < h, columns < w
+        feat = features.as_strided((v, c, s0 // s2, s2 // c), (s0, 1, s2, c))
+    else:
+        feat = ops.pack_features(features, dtype)
+    volume, valid = ops.backproject_per_view(feat, points.to(feat.device), projection.to(feat.device),
+                                             depth, prob, float(voxel_size[-1]), h, w)
+    volume = volume.reshape(v, c, nx, ny, nz) if volume.is_contiguous() else \
+        volume.unflatten(2, (nx, ny, nz))
+    valid = valid.view(v, 1, nx, ny, nz)
+    return volume, valid, torch.tensor(1.), torch.tensor(1.)

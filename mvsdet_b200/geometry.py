@@ -1,0 +1,174 @@
+"""Per-scene camera geometry of the MVSDet hot path, evaluated on the host.
+
+The reference receives the camera matrices as numpy arrays inside ``img_meta``
+and rebuilds small tensors from them every iteration
+(projects/NeRF-Det/nerfdet/mvsdet.py:407-434, :448-450, :1124-1156, :1316-1327).
+All of it is O(V) 4x4 algebra; here it stays on the host in fp32 with the same
+ATen ops (``torch.inverse``, ``matmul``, ``topk``), is packed into ONE pinned
+buffer and uploaded with a single async copy -- the kernels then read a small
+parameter block.  Same names and argument meaning as the reference.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+__all__ = ["knn", "get_nearest_pose_ids", "collect_proj", "homography_params",
+           "compute_projection", "get_points", "feature_intrinsics", "depth_values_for",
+           "SceneGeometry", "scene_geometry"]
+
+
+def knn(x: torch.Tensor, ref: torch.Tensor, k: int, maskself: bool = False) -> torch.Tensor:
+    """Reference: mvsdet.py:43-64.  x, ref [B,3,N] -> [B,N,k] indices of the k
+    nearest points of ``ref`` (largest negated squared distance first)."""
+    neg_d2 = -(ref ** 2).sum(1, keepdim=True) + 2 * torch.matmul(x.transpose(2, 1), ref)
+    neg_d2 = neg_d2 - (x ** 2).sum(1, keepdim=True).transpose(2, 1)
+    if maskself:
+        if x.shape != ref.shape:
+            raise ValueError("maskself needs x and ref of the same shape")
+        eye = torch.arange(x.shape[2])
+        neg_d2[:, eye, eye] = -100000
+    return neg_d2.topk(k=k, dim=-1)[1]
+
+
+def get_nearest_pose_ids(tar_pose: torch.Tensor, ref_poses: torch.Tensor, num_select: int,
+                         maskself: bool = False, angular_dist_method: str = "dist") -> torch.Tensor:
+    """Reference: mvsdet.py:67-104 (only the live ``'dist'`` method).
+    camera-to-world poses [V,4,4] -> neighbour ids [V,k], nearest first."""
+    if angular_dist_method != "dist":
+        raise ValueError("only angular_dist_method='dist' exists on the MVSDet path")
+    num_select = min(num_select, len(ref_poses) - 1)
+    tar = tar_pose[:, :3, 3].unsqueeze(0).transpose(2, 1)
+    ref = ref_poses[:, :3, 3].unsqueeze(0).transpose(2, 1)
+    return knn(tar, ref, k=num_select, maskself=maskself)[0]
+
+
+def feature_intrinsics(intrinsic: torch.Tensor, ratio: float) -> torch.Tensor:
+    """mvsdet.py:422-428: focal lengths / principal point at feature resolution."""
+    k = intrinsic.clone()
+    if k.dim() == 2:
+        k[:2] /= ratio
+    else:
+        k[:, :2] /= ratio
+    return k
+
+
+def collect_proj(w2c: torch.Tensor, intr: torch.Tensor, neighbor_ids: torch.Tensor):
+    """Reference: MVSDet.collect_proj, mvsdet.py:249-264."""
+    if intr.dim() == 2:
+        intr = intr.unsqueeze(0).expand(w2c.shape[0], 4, 4)
+    proj = torch.matmul(intr, w2c)
+    v, k = neighbor_ids.shape
+    nei = proj[neighbor_ids.reshape(-1)].view(v, k, 4, 4)
+    return proj, torch.unbind(nei, dim=1)
+
+
+def homography_params(src_proj: torch.Tensor, ref_proj: torch.Tensor) -> torch.Tensor:
+    """[B,4,4] x2 -> [B,12]: rot rows then trans of src_proj @ inverse(ref_proj)
+    (mvs_models/module.py:116-118), the parameter block the warp kernels read."""
+    m = torch.matmul(src_proj, torch.inverse(ref_proj))
+    return torch.cat((m[:, :3, :3].reshape(-1, 9), m[:, :3, 3]), dim=1).contiguous()
+
+
+def compute_projection(img_meta: dict, stride: int) -> torch.Tensor:
+    """Reference: MVSDet._compute_projection, mvsdet.py:1124-1156 (angles=None).
+    -> [V,3,4] fp32, K_feat[:3,:3] @ w2c[:3] per view."""
+    intr = img_meta["lidar2img"]["intrinsic"]
+    per_view = isinstance(intr, (list, tuple))
+    intr_t = torch.as_tensor(np.array(intr), dtype=torch.float32)
+    extr = torch.as_tensor(np.array(img_meta["lidar2img"]["extrinsic"]), dtype=torch.float32)
+    ratio = img_meta["ori_shape"][0] / (img_meta["img_shape"][0] / stride)
+    out = []
+    for i in range(extr.shape[0]):
+        k = (intr_t[i] if per_view else intr_t)[:3, :3].clone()
+        k[:2] /= ratio
+        out.append(k @ extr[i, :3])
+    return torch.stack(out)
+
+
+def get_points(n_voxels, voxel_size, origin) -> torch.Tensor:
+    """Reference: get_points, mvsdet.py:1316-1327 -> [3,nx,ny,nz] fp32."""
+    n_voxels = torch.as_tensor(n_voxels)
+    voxel_size = torch.as_tensor(voxel_size, dtype=torch.float32)
+    origin = torch.as_tensor(origin, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(*[torch.arange(int(n)) for n in n_voxels], indexing="ij"))
+    new_origin = origin - n_voxels / 2. * voxel_size
+    return grid * voxel_size.view(3, 1, 1, 1) + new_origin.view(3, 1, 1, 1)
+
+
+def depth_values_for(near_far_range: Sequence[float], num_depth: int) -> np.ndarray:
+    """mvsdet.py:222-225."""
+    interval = (near_far_range[1] - near_far_range[0]) / num_depth
+    dv = np.arange(near_far_range[0], near_far_range[1], interval, dtype=np.float32)
+    if len(dv) != num_depth:
+        raise ValueError(f"near_far_range {near_far_range} / {num_depth} planes does not "
+                         f"yield {num_depth} depth values (reference assert, mvsdet.py:225)")
+    return dv
+
+
+@dataclass
+class SceneGeometry:
+    """Device-resident parameter block of one scene."""
+    neighbor_ids: torch.Tensor     # [V,k] int32
+    hom: torch.Tensor              # [V,k,12] fp32
+    depth_values: torch.Tensor     # [V,D] fp32
+    projection: torch.Tensor       # [V,3,4] fp32
+    points: torch.Tensor           # [3,nx,ny,nz] fp32
+    neighbor_ids_host: torch.Tensor  # [V,k] int64 (reference dtype)
+    height: int                    # un-padded feature rows (img_shape[0] // stride)
+    width: int
+    k: int
+
+
+def scene_geometry(img_meta: dict, *, stride: int, near_far_range, num_depth: int, n_voxels,
+                   voxel_size, num_neighbors: int = 2, device="cuda",
+                   view_slice: Optional[slice] = None) -> SceneGeometry:
+    """Everything mvsdet.py:407-450 derives from ``img_meta``, packed and uploaded
+    with one pinned async copy.  ``view_slice`` restricts the *reference* views
+    (rows of every per-view array) for view-sharded multi-GPU runs; neighbour
+    ids keep indexing the full feature tensor."""
+    extr = img_meta["lidar2img"]["extrinsic"]
+    w2c = torch.as_tensor(np.array(extr), dtype=torch.float32)
+    v_all = w2c.shape[0]
+    intr = torch.as_tensor(np.array(img_meta["lidar2img"]["intrinsic"]), dtype=torch.float32)
+    ratio = img_meta["ori_shape"][0] / (img_meta["img_shape"][0] / stride)
+    k_feat = feature_intrinsics(intr, ratio)
+    k = min(num_neighbors, v_all - 1)
+    c2w = w2c.inverse()
+    nbr = get_nearest_pose_ids(c2w, c2w, k, maskself=True)            # [V,k] int64
+    ref_proj, nei_projs = collect_proj(w2c, k_feat, nbr)
+    if k > 0:
+        hom = torch.stack([homography_params(np_, ref_proj) for np_ in nei_projs], dim=1)
+    else:
+        hom = torch.zeros(v_all, 0, 12)
+    dvals = torch.as_tensor(depth_values_for(near_far_range, num_depth)).unsqueeze(0).repeat(v_all, 1)
+    projection = compute_projection(img_meta, stride)
+    points = get_points(n_voxels, voxel_size, img_meta["lidar2img"]["origin"])
+    if view_slice is not None:
+        nbr, hom, dvals, projection = nbr[view_slice], hom[view_slice], dvals[view_slice], projection[view_slice]
+
+    parts = [nbr.to(torch.int32).reshape(-1).view(torch.float32) if nbr.numel() else torch.zeros(0),
+             hom.reshape(-1), dvals.reshape(-1), projection.reshape(-1), points.reshape(-1)]
+    sizes = [p.numel() for p in parts]
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        staging = torch.empty(sum(sizes), dtype=torch.float32, pin_memory=True)
+        torch.cat(parts, out=staging)
+        blob = staging.to(dev, non_blocking=True)
+    else:
+        blob = torch.cat(parts)
+    o = np.cumsum([0] + sizes)
+    v = nbr.shape[0]
+    return SceneGeometry(
+        neighbor_ids=blob[o[0]:o[1]].view(torch.int32).view(v, k),
+        hom=blob[o[1]:o[2]].view(v, k, 12),
+        depth_values=blob[o[2]:o[3]].view(v, num_depth),
+        projection=blob[o[3]:o[4]].view(v, 3, 4),
+        points=blob[o[4]:o[5]].view(3, *[int(n) for n in n_voxels]),
+        neighbor_ids_host=nbr,
+        height=img_meta["img_shape"][0] // stride,
+        width=img_meta["img_shape"][1] // stride,
+        k=k)

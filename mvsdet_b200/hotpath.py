@@ -1,0 +1,100 @@
+"""Drop-in replacement for the per-scene block of ``MVSDet.extract_feat``
+(projects/NeRF-Det/nerfdet/mvsdet.py:404-515 and :681-682).
+
+``MVSDetHotPath`` takes what that block takes -- one scene's FPN features
+[V,C,Hf,Wf], its ``img_meta`` and the cost-regularisation net -- and returns
+what it produces (volume_mean, per-voxel valid count, the depth hypotheses and
+probabilities the NVS branch consumes), but runs three fused kernels instead
+of ~150 ATen launches with host syncs:
+
+    features --pack--> channels-last (fp32 | bf16)
+        plane_sweep_variance            mvsdet.py:439-467
+        cost_regularization (cuDNN)     mvsdet.py:470   (not part of the path)
+        depth_topk                      mvsdet.py:472-482, :266-283, :298-317
+        backproject_aggregate           mvsdet.py:499-515, :681-682
+
+Constructor arguments are the detector's own (mvsdet.py:125-155):
+``near_far_range``, ``num_monocular_samples`` (gs_cfg), ``topk``, ``n_voxels``,
+``voxel_size``.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .geometry import SceneGeometry, scene_geometry
+
+__all__ = ["MVSDetHotPath"]
+
+
+class MVSDetHotPath(nn.Module):
+    def __init__(self, n_voxels: Sequence[int], voxel_size: Sequence[float],
+                 near_far_range: Sequence[float], num_monocular_samples: int = 12, topk: int = 3,
+                 cost_regularization: Optional[nn.Module] = None, stride: int = 4,
+                 feature_dtype: torch.dtype = torch.float32,
+                 variance_dtype: torch.dtype = torch.float32,
+                 channels_first_volume: bool = True, num_neighbors: int = 2):
+        super().__init__()
+        self.n_voxels = [int(n) for n in n_voxels]
+        self.voxel_size = [float(s) for s in voxel_size]
+        self.near_far_range = [float(x) for x in near_far_range]
+        self.num_depth = int(num_monocular_samples)
+        # mvsdet.py:222 -- python float, becomes fp32 inside the ops
+        self.depth_interval = (self.near_far_range[1] - self.near_far_range[0]) / self.num_depth
+        self.topk = int(topk)
+        self.stride = int(stride)
+        self.cost_regularization = cost_regularization
+        self.feature_dtype = feature_dtype
+        self.variance_dtype = variance_dtype
+        self.channels_first_volume = channels_first_volume
+        self.num_neighbors = num_neighbors      # k = min(2, V-1), mvsdet.py:432
+
+    def geometry(self, img_meta: dict, device, view_slice=None) -> SceneGeometry:
+        return scene_geometry(img_meta, stride=self.stride, near_far_range=self.near_far_range,
+                              num_depth=self.num_depth, n_voxels=self.n_voxels,
+                              voxel_size=self.voxel_size, num_neighbors=self.num_neighbors,
+                              device=device, view_slice=view_slice)
+
+    # -- stages ------------------------------------------------------------
+    def variance(self, feat_cl: torch.Tensor, geo: SceneGeometry, ref_begin: int = 0) -> torch.Tensor:
+        return ops.plane_sweep_variance(feat_cl, geo.neighbor_ids, geo.hom, geo.depth_values,
+                                        out_dtype=self.variance_dtype, ref_begin=ref_begin)
+
+    def hypotheses(self, cost_out: torch.Tensor):
+        return ops.depth_topk(cost_out, self.near_far_range[0], self.depth_interval, self.topk)
+
+    def voxels(self, feat_cl, geo: SceneGeometry, est_depth, est_dens, mode: str = "mean"):
+        return ops.backproject_aggregate(feat_cl, geo.points, geo.projection, est_depth, est_dens,
+                                         self.voxel_size[2], geo.height, geo.width, mode=mode,
+                                         channels_first=self.channels_first_volume)
+
+    # -- the whole block ---------------------------------------------------
+    def forward(self, feature: torch.Tensor, img_meta: dict,
+                cost_regularization: Optional[Callable] = None,
+                geometry: Optional[SceneGeometry] = None) -> Dict[str, torch.Tensor]:
+        """feature [V,C,Hf,Wf] (fp32 NCHW as the reference's FPN gives it, or
+        already channels_last / bf16).  Returns a dict with
+          volume_mean [C,nx,ny,nz], valid [1,nx,ny,nz] (float count, as
+          extract_feat returns it, mvsdet.py:698), count int32 [N],
+          variance, prob_volume, off_pred, est_depth, est_densities, est_idx,
+          depth_coding [V,1,h,w] -- the reference's intermediates."""
+        cost_net = cost_regularization or self.cost_regularization
+        if cost_net is None:
+            raise ValueError("a cost_regularization callable is required (mvsdet.py:470)")
+        geo = geometry or self.geometry(img_meta, feature.device)
+        feat_cl = ops.pack_features(feature, self.feature_dtype)
+        variance = self.variance(feat_cl, geo)
+        cost_out = cost_net(variance)
+        prob, off, est_depth, est_dens, est_idx, coding = self.hypotheses(cost_out)
+        vol, count = self.voxels(feat_cl, geo, est_depth, est_dens)
+        nx, ny, nz = self.n_voxels
+        c = feat_cl.shape[1]
+        volume_mean = vol.view(c, nx, ny, nz) if vol.is_contiguous() else vol.unflatten(1, (nx, ny, nz))
+        return dict(volume_mean=volume_mean, valid=count.view(1, nx, ny, nz).float(), count=count,
+                    variance=variance, prob_volume=prob, off_pred=off, est_depth=est_depth,
+                    est_densities=est_dens, est_idx=est_idx,
+                    depth_coding=coding[:, :geo.height, :geo.width].unsqueeze(1),
+                    neighbor_ids=geo.neighbor_ids_host)

@@ -1,0 +1,472 @@
+"""PyTorch custom-op layer over the C ABI (include/mvsdet_b200.h).
+
+Each op is a ``torch.autograd.Function`` whose forward and backward enqueue the
+hand-written sm_100a kernels on ``torch.cuda.current_stream()`` through ctypes;
+PyTorch only owns the memory.  There is deliberately no CPU / eager fallback:
+a CPU tensor is a ``ValueError`` and a missing library an exception at first
+use.
+
+Tensor conventions: feature maps have logical shape [V,C,H,W] in
+``torch.channels_last`` memory format; volumes have logical shape [V,C,D,H,W]
+in ``torch.channels_last_3d`` -- the reference's logical shapes
+(mvs_models/module.py:105-111, mvsdet.py:439-467), with the memory format the
+kernels (and cuDNN's Conv3d after them) want.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (BF16, BP_MEAN, BP_PER_VIEW, BP_SUM, CHANNELS_FIRST, CHANNELS_LAST, F32)
+
+__all__ = ["pack_features", "plane_sweep_variance", "homo_warp", "depth_topk", "topk_hypotheses",
+           "backproject_aggregate", "backproject_per_view", "voxel_normalize"]
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise ValueError(f"mvsdet_b200 kernels take float32 or bfloat16, got {dtype}")
+
+
+def _need_cuda(name: str, t: torch.Tensor) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor: mvsdet_b200 has no CPU path")
+
+
+def _is_nhwc(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous()
+
+
+def _is_ndhwc(t: torch.Tensor) -> bool:
+    return t.dim() == 5 and t.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def _empty_nhwc(v, c, h, w, dtype, device) -> torch.Tensor:
+    return torch.empty((v, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def _zeros_nhwc(v, c, h, w, dtype, device) -> torch.Tensor:
+    return torch.zeros((v, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def _empty_ndhwc(v, c, d, h, w, dtype, device) -> torch.Tensor:
+    return torch.empty((v, d, h, w, c), dtype=dtype, device=device).permute(0, 4, 1, 2, 3)
+
+
+def _as_ndhwc(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t if _is_ndhwc(t) else t.contiguous(memory_format=torch.channels_last_3d)
+
+
+# --------------------------------------------------------------------------
+# layout: [V,C,H,W] fp32 contiguous <-> channels-last
+# --------------------------------------------------------------------------
+class _PackFeatures(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, dtype: torch.dtype):
+        v, c, h, w = x.shape
+        out = _empty_nhwc(v, c, h, w, dtype, x.device)
+        _lib.call("mvsd_pack_nchw_to_nhwc", x.data_ptr(), out.data_ptr(), _code(dtype),
+                  v, c, h, w, _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        v, c, h, w = g.shape
+        if g.dtype != torch.float32 or not _is_nhwc(g):
+            g = g.float().contiguous(memory_format=torch.channels_last)
+        out = torch.empty((v, c, h, w), dtype=torch.float32, device=g.device)
+        _lib.call("mvsd_unpack_nhwc_to_nchw", g.data_ptr(), out.data_ptr(), 0, v, c, h, w, _stream())
+        return out, None
+
+
+def pack_features(x: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """[V,C,H,W] features -> the same logical tensor in channels_last memory
+    format and ``dtype`` (fp32 or bf16).  A tensor that already has that layout
+    and dtype is returned as is; an fp32 NCHW-contiguous tensor (the reference's
+    FPN output, mvsdet.py:373-376) goes through the transpose kernel."""
+    _need_cuda("features", x)
+    if x.dim() != 4:
+        raise ValueError("features must be [V,C,H,W]")
+    if _is_nhwc(x) and x.shape[1] > 1:
+        return x if x.dtype == dtype else x.to(dtype)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    return _PackFeatures.apply(x, dtype)
+
+
+# --------------------------------------------------------------------------
+# plane sweep
+# --------------------------------------------------------------------------
+class _PlaneSweepVariance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, nbr_ids, hom, depth_values, out_dtype, ref_begin):
+        _, c, h, w = feat.shape
+        v = nbr_ids.shape[0]
+        d = depth_values.shape[1]
+        k = nbr_ids.shape[1]
+        out = _empty_ndhwc(v, c, d, h, w, out_dtype, feat.device)
+        _lib.call("mvsd_plane_sweep_fwd", feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids),
+                  _ptr(hom), depth_values.data_ptr(), out.data_ptr(), _code(out_dtype),
+                  CHANNELS_LAST, v, c, d, h, w, k, ref_begin, _stream())
+        ctx.save_for_backward(feat, nbr_ids, hom, depth_values)
+        ctx.ref_begin = ref_begin
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, nbr_ids, hom, depth_values = ctx.saved_tensors
+        vf, c, h, w = feat.shape
+        v = nbr_ids.shape[0]
+        d = depth_values.shape[1]
+        k = nbr_ids.shape[1]
+        gdt = torch.bfloat16 if (g.dtype == torch.bfloat16 and feat.dtype == torch.bfloat16) else torch.float32
+        g = _as_ndhwc(g, gdt)
+        g_feat = _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
+        _lib.call("mvsd_plane_sweep_bwd", g.data_ptr(), _code(g.dtype), CHANNELS_LAST,
+                  feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids), _ptr(hom),
+                  depth_values.data_ptr(), g_feat.data_ptr(), v, c, d, h, w, k, ctx.ref_begin,
+                  _stream())
+        g_feat = g_feat.to(feat.dtype) if feat.dtype != torch.float32 else g_feat
+        return g_feat, None, None, None, None, None
+
+
+def plane_sweep_variance(feat: torch.Tensor, nbr_ids: torch.Tensor, hom: torch.Tensor,
+                         depth_values: torch.Tensor,
+                         out_dtype: torch.dtype = torch.float32,
+                         ref_begin: int = 0) -> torch.Tensor:
+    """Fused mvsdet.py:439-467: channels-last features [Vf,C,H,W] (fp32/bf16),
+    neighbour ids [V,k] int32 (indices into feat), homographies [V,k,12], depth
+    planes [V,D] -> variance volume, logical [V,C,D,H,W] in channels_last_3d.
+    Reference view v is feat[ref_begin + v]; V < Vf sweeps a slice of the views
+    (view-sharded multi-GPU)."""
+    for n, t in (("feat", feat), ("nbr_ids", nbr_ids), ("hom", hom), ("depth_values", depth_values)):
+        _need_cuda(n, t)
+    if not _is_nhwc(feat):
+        raise ValueError("feat must be channels_last; use ops.pack_features")
+    if nbr_ids.dtype != torch.int32 or not nbr_ids.is_contiguous():
+        raise ValueError("nbr_ids must be contiguous int32 [V,k]")
+    v, k = nbr_ids.shape
+    if tuple(hom.shape) != (v, k, 12) or depth_values.shape[0] != v:
+        raise ValueError("nbr_ids [V,k], hom [V,k,12] and depth_values [V,D] must agree")
+    if ref_begin < 0 or ref_begin + v > feat.shape[0]:
+        raise ValueError("reference views [ref_begin, ref_begin+V) exceed feat")
+    if hom.dtype != torch.float32 or depth_values.dtype != torch.float32:
+        raise ValueError("hom and depth_values must be float32")
+    return _PlaneSweepVariance.apply(feat, nbr_ids, hom.contiguous(), depth_values.contiguous(),
+                                     out_dtype, int(ref_begin))
+
+
+class _HomoWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, hom, depth_values, out_dtype):
+        b, c, h, w = src.shape
+        d = depth_values.shape[1]
+        out = _empty_ndhwc(b, c, d, h, w, out_dtype, src.device)
+        _lib.call("mvsd_homo_warp_fwd", src.data_ptr(), _code(src.dtype), hom.data_ptr(),
+                  depth_values.data_ptr(), out.data_ptr(), _code(out_dtype), CHANNELS_LAST,
+                  b, c, d, h, w, _stream())
+        ctx.save_for_backward(hom, depth_values)
+        ctx.src_meta = (src.shape, src.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        hom, depth_values = ctx.saved_tensors
+        (b, c, h, w), sdtype = ctx.src_meta
+        d = depth_values.shape[1]
+        g = _as_ndhwc(g, torch.float32 if g.dtype != torch.bfloat16 else torch.bfloat16)
+        g_src = _zeros_nhwc(b, c, h, w, torch.float32, g.device)
+        _lib.call("mvsd_homo_warp_bwd", g.data_ptr(), _code(g.dtype), CHANNELS_LAST, hom.data_ptr(),
+                  depth_values.data_ptr(), g_src.data_ptr(), b, c, d, h, w, _stream())
+        return (g_src if sdtype == torch.float32 else g_src.to(sdtype)), None, None, None
+
+
+def homo_warp(src: torch.Tensor, hom: torch.Tensor, depth_values: torch.Tensor,
+              out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """mvs_models/module.py:105-146 with the homography already reduced to
+    [B,12] (rot rows, trans): channels-last [B,C,H,W] -> [B,C,D,H,W]."""
+    for n, t in (("src", src), ("hom", hom), ("depth_values", depth_values)):
+        _need_cuda(n, t)
+    if not _is_nhwc(src):
+        raise ValueError("src must be channels_last; use ops.pack_features")
+    return _HomoWarp.apply(src, hom.contiguous().float(), depth_values.contiguous().float(), out_dtype)
+
+
+# --------------------------------------------------------------------------
+# softmax / sigmoid / top-k / expectation
+# --------------------------------------------------------------------------
+def _cost_strides(cost_out: torch.Tensor):
+    """(tensor, s_v, s_c, s_d, s_p) for NCDHW-contiguous or channels_last_3d."""
+    v, two, d, h, w = cost_out.shape
+    if cost_out.dtype != torch.float32:
+        cost_out = cost_out.float()
+    sv, sc, sd, sh, sw = cost_out.stride()
+    if sh != w * sw or (cost_out.numel() and min(sv, sc, sd, sw) < 1):
+        cost_out = cost_out.contiguous()
+        sv, sc, sd, sh, sw = cost_out.stride()
+    return cost_out, sv, sc, sd, sw
+
+
+class _DepthTopk(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cost_out, near, interval, topk, raw):
+        cost_out, sv, sc, sd, sp = _cost_strides(cost_out)
+        v, _, d, h, w = cost_out.shape
+        dev = cost_out.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        prob = torch.empty((v, d, h, w), **f32)
+        off = torch.empty((v, d, h, w), **f32)
+        est_depth = torch.empty((v, topk, h, w), **f32)
+        est_dens = torch.empty((v, topk, h, w), **f32)
+        est_idx = torch.empty((v, topk, h, w), dtype=torch.int64, device=dev)
+        coding = torch.empty((v, h, w), **f32)
+        _lib.call("mvsd_depth_topk_fwd", cost_out.data_ptr(), sv, sc, sd, sp, prob.data_ptr(),
+                  off.data_ptr(), est_depth.data_ptr(), est_dens.data_ptr(), est_idx.data_ptr(),
+                  coding.data_ptr(), float(near), float(interval), int(raw), v, d, h, w, topk, _stream())
+        ctx.save_for_backward(cost_out, est_idx)
+        ctx.consts = (float(near), float(interval), topk, int(raw))
+        ctx.mark_non_differentiable(est_idx)
+        return prob, off, est_depth, est_dens, est_idx, coding
+
+    @staticmethod
+    def backward(ctx, g_prob, g_off, g_depth, g_dens, _g_idx, g_coding):
+        cost_out, est_idx = ctx.saved_tensors
+        near, interval, topk, raw = ctx.consts
+        cost_out, sv, sc, sd, sp = _cost_strides(cost_out)
+        v, _, d, h, w = cost_out.shape
+
+        def prep(g):
+            return None if g is None else g.contiguous().float()
+        g_prob, g_off, g_depth, g_dens, g_coding = map(prep, (g_prob, g_off, g_depth, g_dens, g_coding))
+        g_cost = torch.empty((v, 2, d, h, w), dtype=torch.float32, device=cost_out.device)
+        _lib.call("mvsd_depth_topk_bwd", cost_out.data_ptr(), sv, sc, sd, sp, est_idx.data_ptr(),
+                  _ptr(g_prob), _ptr(g_off), _ptr(g_depth), _ptr(g_dens), _ptr(g_coding),
+                  g_cost.data_ptr(), near, interval, raw, v, d, h, w, topk, _stream())
+        return g_cost, None, None, None, None
+
+
+def depth_topk(cost_out: torch.Tensor, near: float, interval: float, topk: int):
+    """Fused mvsdet.py:470-482 + sample_depth_prob (:266-283) + compute_avg_depth
+    (:298-317).  cost_out [V,2,D,H,W] -> (prob_volume [V,D,H,W], off_pred
+    [V,D,H,W], est_depth [V,T,H,W], est_densities [V,T,H,W], est_idx int64
+    [V,T,H,W], depth_coding [V,H,W])."""
+    _need_cuda("cost_out", cost_out)
+    if cost_out.dim() != 5 or cost_out.shape[1] != 2:
+        raise ValueError("cost_out must be [V,2,D,H,W]")
+    return _DepthTopk.apply(cost_out, near, interval, int(topk), 0)
+
+
+def topk_hypotheses(prob_off: torch.Tensor, near: float, interval: float, topk: int):
+    """Stand-alone form of ``depth_topk`` for inputs that are already
+    probabilities / offsets: prob_off [V,2,D,H,W] = stack(prob_volume, off_pred).
+    Same six outputs (the first two are pass-through copies)."""
+    _need_cuda("prob_off", prob_off)
+    if prob_off.dim() != 5 or prob_off.shape[1] != 2:
+        raise ValueError("prob_off must be [V,2,D,H,W]")
+    return _DepthTopk.apply(prob_off, near, interval, int(topk), 1)
+
+
+# --------------------------------------------------------------------------
+# back-projection
+# --------------------------------------------------------------------------
+def _zeros_strided_like(t: torch.Tensor) -> torch.Tensor:
+    """zeros with exactly t's sizes AND strides (zeros_like falls back to
+    contiguous strides for views with gaps, e.g. a row-cropped map)."""
+    return torch.empty_strided(t.size(), t.stride(), dtype=t.dtype, device=t.device).zero_()
+
+
+class _BackprojectAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, points, projection, est_depth, est_dens, vs_z, h, w, mode, channels_first):
+        v, c, fh, fw = feat.shape
+        t = est_depth.shape[1]
+        n = points.numel() // 3
+        dev = feat.device
+        sv, st, sy, sx = est_depth.stride()
+        if channels_first:
+            out = torch.empty((c, n), dtype=torch.float32, device=dev)
+        else:
+            out = torch.empty((n, c), dtype=torch.float32, device=dev)
+        count = torch.empty((n,), dtype=torch.int32, device=dev)
+        _lib.call("mvsd_backproject_fwd", feat.data_ptr(), _code(feat.dtype), fh, fw,
+                  points.data_ptr(), projection.data_ptr(), est_depth.data_ptr(),
+                  est_dens.data_ptr(), sv, sy, sx, st, float(vs_z), mode, out.data_ptr(),
+                  CHANNELS_FIRST if channels_first else CHANNELS_LAST, count.data_ptr(), None,
+                  None, v, c, h, w, t, n, _stream())
+        ctx.save_for_backward(feat, points, projection, est_depth, est_dens, count)
+        ctx.consts = (float(vs_z), h, w, mode, channels_first)
+        ctx.mark_non_differentiable(count)
+        res = out if channels_first else out.t()
+        return res, count
+
+    @staticmethod
+    def backward(ctx, g_out, _g_count):
+        feat, points, projection, est_depth, est_dens, count = ctx.saved_tensors
+        vs_z, h, w, mode, channels_first = ctx.consts
+        v, c, fh, fw = feat.shape
+        t = est_depth.shape[1]
+        n = points.numel() // 3
+        sv, st, sy, sx = est_depth.stride()
+        g_out = g_out.float()
+        g_mem = g_out.contiguous() if channels_first else g_out.t().contiguous()
+        g_feat = _zeros_nhwc(v, c, fh, fw, torch.float32, feat.device)
+        g_pn = _zeros_strided_like(est_dens)
+        g_prob = _zeros_strided_like(est_dens)
+        _lib.call("mvsd_backproject_bwd", g_mem.data_ptr(),
+                  CHANNELS_FIRST if channels_first else CHANNELS_LAST, mode, count.data_ptr(),
+                  feat.data_ptr(), _code(feat.dtype), fh, fw, points.data_ptr(),
+                  projection.data_ptr(), est_depth.data_ptr(), est_dens.data_ptr(),
+                  sv, sy, sx, st, vs_z, g_feat.data_ptr(), g_pn.data_ptr(),
+                  v, c, h, w, t, n, _stream())
+        _lib.call("mvsd_prob_norm_bwd", est_dens.data_ptr(), g_pn.data_ptr(), g_prob.data_ptr(),
+                  sv, sy, sx, st, v, h, w, t, _stream())
+        g_feat = g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)
+        return g_feat, None, None, None, g_prob, None, None, None, None, None
+
+
+def _check_hyp(name, t, v, fh, fw):
+    _need_cuda(name, t)
+    if t.dim() != 4 or t.shape[0] != v or t.shape[2] != fh or t.shape[3] != fw:
+        raise ValueError(f"{name} must be [V,T,{fh},{fw}] (the full, un-cropped map)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32")
+
+
+def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: float,
+                          height: int, width: int, *, mode: str = "mean",
+                          channels_first: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused backproject_Weigh (mvsdet.py:1372-1492) + aggregation (:511-515,
+    :681-682).
+
+    feat        channels-last [V,C,Hf,Wf] (only [:height,:width] is addressed)
+    points      [3,nx,ny,nz] fp32;  projection [V,3,4] fp32
+    est_depth, est_dens   [V,T,Hf,Wf] fp32 as ``depth_topk`` returns them
+    mode        "mean" -> (volume_mean [C,N], count [N] int32)
+                "sum"  -> (volume_sum  [C,N], count) partials for multi-GPU
+    The result is logical [C,N]; with channels_first=False its memory is [N,C]
+    (channels_last_3d once viewed as [C,nx,ny,nz])."""
+    _need_cuda("feat", feat)
+    if not _is_nhwc(feat):
+        raise ValueError("feat must be channels_last; use ops.pack_features")
+    v, c, fh, fw = feat.shape
+    _check_hyp("est_depth", est_depth, v, fh, fw)
+    _check_hyp("est_dens", est_dens, v, fh, fw)
+    if est_depth.stride() != est_dens.stride():
+        est_depth, est_dens = est_depth.contiguous(), est_dens.contiguous()
+    _need_cuda("points", points)
+    _need_cuda("projection", projection)
+    if tuple(projection.shape) != (v, 3, 4):
+        raise ValueError("projection must be [V,3,4]")
+    if height > fh or width > fw:
+        raise ValueError("crop exceeds the feature map")
+    m = {"mean": BP_MEAN, "sum": BP_SUM}[mode]
+    return _BackprojectAggregate.apply(feat, points.contiguous().float(),
+                                       projection.contiguous().float(), est_depth, est_dens,
+                                       float(vs_z), int(height), int(width), m, bool(channels_first))
+
+
+class _BackprojectPerView(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, points, projection, depth, prob, vs_z, h, w, strides):
+        v, c, fh, fw = feat.shape
+        n = points.numel() // 3
+        t = strides[4]
+        dev = feat.device
+        out = torch.zeros((v, n, c), dtype=torch.float32, device=dev)
+        valid = torch.empty((v, n), dtype=torch.uint8, device=dev)
+        _lib.call("mvsd_backproject_fwd", feat.data_ptr(), _code(feat.dtype), fh, fw,
+                  points.data_ptr(), projection.data_ptr(), depth.data_ptr(), prob.data_ptr(),
+                  strides[0], strides[1], strides[2], strides[3], float(vs_z), BP_PER_VIEW,
+                  out.data_ptr(), CHANNELS_LAST, None, valid.data_ptr(), None,
+                  v, c, h, w, t, n, _stream())
+        ctx.save_for_backward(feat, points, projection, depth, prob)
+        ctx.consts = (float(vs_z), h, w, strides)
+        valid = valid.bool()
+        ctx.mark_non_differentiable(valid)
+        return out.permute(0, 2, 1), valid
+
+    @staticmethod
+    def backward(ctx, g_out, _g_valid):
+        feat, points, projection, depth, prob = ctx.saved_tensors
+        vs_z, h, w, strides = ctx.consts
+        v, c, fh, fw = feat.shape
+        n = points.numel() // 3
+        t = strides[4]
+        g_mem = g_out.float().permute(0, 2, 1).contiguous()
+        g_feat = _zeros_nhwc(v, c, fh, fw, torch.float32, feat.device)
+        g_pn = _zeros_strided_like(prob)
+        g_prob = _zeros_strided_like(prob)
+        _lib.call("mvsd_backproject_bwd", g_mem.data_ptr(), CHANNELS_LAST, BP_PER_VIEW, None,
+                  feat.data_ptr(), _code(feat.dtype), fh, fw, points.data_ptr(),
+                  projection.data_ptr(), depth.data_ptr(), prob.data_ptr(),
+                  strides[0], strides[1], strides[2], strides[3], vs_z, g_feat.data_ptr(),
+                  g_pn.data_ptr(), v, c, h, w, t, n, _stream())
+        _lib.call("mvsd_prob_norm_bwd", prob.data_ptr(), g_pn.data_ptr(), g_prob.data_ptr(),
+                  strides[0], strides[1], strides[2], strides[3], v, h, w, t, _stream())
+        g_feat = g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)
+        return g_feat, None, None, None, g_prob, None, None, None, None
+
+
+def backproject_per_view(feat, points, projection, depth, prob, vs_z: float, height: int,
+                         width: int):
+    """Un-aggregated back-projection with the reference's argument layout:
+    ``depth`` / ``prob`` are [V, height*width, num_surface, T] (any strides with
+    a common layout, mvsdet.py:484,495).  Returns (volume logical [V,C,N] with
+    memory [V,N,C], valid bool [V,N])."""
+    _need_cuda("feat", feat)
+    if not _is_nhwc(feat):
+        raise ValueError("feat must be channels_last; use ops.pack_features")
+    v = feat.shape[0]
+    if depth.shape != prob.shape or depth.dim() != 4 or depth.shape[0] != v \
+            or depth.shape[1] != height * width:
+        raise ValueError("depth and prob must be [V, h*w, num_surface, T]")
+    t = depth.shape[2] * depth.shape[3]
+    depth = depth.float()
+    prob = prob.float()
+    if depth.shape[2] != 1 or depth.stride() != prob.stride():
+        depth = depth.reshape(v, height * width, 1, t).contiguous()
+        prob = prob.reshape(v, height * width, 1, t).contiguous()
+    sv, sp, _, st = depth.stride()
+    strides = (sv, sp * width, sp, st, t)
+    return _BackprojectPerView.apply(feat, points.contiguous().float(),
+                                     projection.contiguous().float(), depth, prob, float(vs_z),
+                                     int(height), int(width), strides)
+
+
+def voxel_normalize(volume_sum: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
+    """sum / (count + 1e-8), zero where count == 0 (mvsdet.py:514-515) for a
+    [C,N] (either memory order) partial sum after the multi-GPU all-reduce."""
+    _need_cuda("volume_sum", volume_sum)
+    c, n = volume_sum.shape
+    if volume_sum.is_contiguous():
+        out = torch.empty_like(volume_sum)
+        _lib.call("mvsd_voxel_normalize", volume_sum.data_ptr(), count.data_ptr(), out.data_ptr(),
+                  CHANNELS_FIRST, c, n, _stream())
+        return out
+    mem = volume_sum.t()
+    if not mem.is_contiguous():
+        raise ValueError("volume_sum must be [C,N] contiguous or the transpose of [N,C]")
+    out = torch.empty_like(mem)
+    _lib.call("mvsd_voxel_normalize", mem.data_ptr(), count.data_ptr(), out.data_ptr(),
+              CHANNELS_LAST, c, n, _stream())
+    return out.t()

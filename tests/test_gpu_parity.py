@@ -1,0 +1,215 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI, against the
+CPU oracle and the golden vectors produced by the reference.
+
+Bars (BASELINE.json north_star): voxel indices / valid masks / counts and top-k
+selections bit-exact; variance, probabilities and voxel features within 1e-4
+relative in fp32 (1e-2 with bf16 features).  Float comparisons use
+|a-b| <= atol + rtol*|ref| with rtol = 1e-4 and atol = 1e-4 * rms(ref), so
+entries that cancel to ~0 (variance of three equal samples) are judged against
+the tensor's scale, as SURVEY.md "hard part 4" asks.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, load_golden, oracle_chain
+from oracle import mvsdet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _close(a, b, what, rtol=RTOL, atol_scale=1e-4):
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a)).double()
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b)).double()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    rms = float(b.pow(2).mean().sqrt()) if b.numel() else 0.0
+    tol = atol_scale * max(rms, 1e-30) + rtol * b.abs()
+    err = (a - b).abs()
+    bad = err > tol
+    assert not bool(bad.any()), (
+        f"{what}: {int(bad.sum())}/{bad.numel()} out of tolerance; max abs err "
+        f"{float(err.max()):.3e} (rms ref {rms:.3e})")
+
+
+def _module(cfg, feature_dtype=torch.float32, channels_first=True):
+    from mvsdet_b200.hotpath import MVSDetHotPath
+    return MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
+                         stride=cfg.stride, feature_dtype=feature_dtype,
+                         channels_first_volume=channels_first)
+
+
+def cuda_chain(scene, feature_dtype=torch.float32, channels_first=True, with_grads=True):
+    cfg = scene["cfg"]
+    dev = torch.device("cuda")
+    feature = scene["feature"].to(dev).requires_grad_(with_grads)
+    cost_out = scene["cost_out"].to(dev).requires_grad_(with_grads)
+    mod = _module(cfg, feature_dtype, channels_first)
+    res = mod(feature, scene["img_meta"], cost_regularization=lambda var: cost_out)
+    if with_grads:
+        g1, = torch.autograd.grad(res["variance"], feature, scene["g_variance"].to(dev),
+                                  retain_graph=True)
+        g2, g3 = torch.autograd.grad(res["volume_mean"], (feature, cost_out),
+                                     scene["g_volume_mean"].to(dev))
+        res["g_feature_from_variance"], res["g_feature_from_voxels"], res["g_cost_out"] = g1, g2, g3
+    torch.cuda.synchronize()
+    return res
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("channels_first", [True, False])
+def test_chain_fp32_vs_reference_golden(case, channels_first):
+    scene, gold = load_golden(case)
+    res = cuda_chain(scene, channels_first=channels_first)
+    # integers: bit-exact
+    assert np.array_equal(res["neighbor_ids"].cpu().numpy(), gold["neighbor_ids"])
+    assert np.array_equal(res["est_idx"].cpu().numpy(), gold["est_idx"])
+    assert np.array_equal(res["count"].cpu().numpy().reshape(gold["count"].shape), gold["count"])
+    # floats
+    for key in ("variance", "prob_volume", "off_pred", "est_depth", "est_densities",
+                "depth_coding", "volume_mean"):
+        _close(res[key], gold[key], f"{case}:{key}")
+    for key in ("g_feature_from_variance", "g_feature_from_voxels", "g_cost_out"):
+        _close(res[key], gold[key], f"{case}:{key}")
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES[:2])
+def test_chain_bf16_features(case):
+    """bf16 features / fp32 accumulation (BASELINE.json configs[1]).  The oracle
+    is fed the same bf16-rounded features, so what is tested is the kernel's
+    fp32 arithmetic on bf16 inputs; the 1e-2 bar of the north star covers the
+    bf16-rounded gradient that autograd hands back."""
+    scene, _ = load_golden(case)
+    scene = dict(scene)
+    scene["feature"] = scene["feature"].to(torch.bfloat16).float()
+    ref = oracle_chain(scene)
+    res = cuda_chain(scene, feature_dtype=torch.bfloat16)
+    assert np.array_equal(res["count"].cpu().numpy().reshape(ref["count"].shape), ref["count"].numpy())
+    assert np.array_equal(res["est_idx"].cpu().numpy(), ref["est_idx"].numpy())
+    for key in ("variance", "volume_mean", "est_depth", "est_densities"):
+        _close(res[key], ref[key], f"{case}:{key}")
+    for key in ("g_feature_from_variance", "g_feature_from_voxels"):
+        _close(res[key], ref[key], f"{case}:{key}", rtol=1e-2, atol_scale=1e-2)
+    _close(res["g_cost_out"], ref["g_cost_out"], f"{case}:g_cost_out")
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_homo_warping_mirror(case):
+    """functional.homo_warping keeps the reference signature
+    (mvs_models/module.py:105) and values."""
+    from mvsdet_b200 import functional as F_
+    scene, gold = load_golden(case)
+    feat = scene["feature"]
+    nbr = torch.from_numpy(gold["neighbor_ids"])
+    ref_proj = torch.from_numpy(gold["ref_proj"])
+    nei_proj = torch.from_numpy(gold["nei_projs"])[0]
+    cfg = scene["cfg"]
+    dv = torch.from_numpy(O.depth_values_for(cfg.near_far_range, cfg.num_depth))
+    dv = dv.unsqueeze(0).repeat(feat.shape[0], 1)
+    src = feat[nbr[:, 0]].clone().requires_grad_(True)
+    want = O.homo_warping(src, nei_proj, ref_proj, dv)
+    g = torch.randn(want.shape, generator=torch.Generator().manual_seed(5))
+    gw, = torch.autograd.grad(want, src, g)
+    src_c = src.detach().cuda().requires_grad_(True)
+    got = F_.homo_warping(src_c, nei_proj.cuda(), ref_proj.cuda(), dv.cuda())
+    assert tuple(got.shape) == tuple(want.shape)
+    _close(got, want, f"{case}:warped")
+    _close(got[:, :4], gold["warped0"], f"{case}:warped vs golden")
+    gg, = torch.autograd.grad(got, src_c, g.cuda())
+    _close(gg, gw, f"{case}:g_src")
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_backproject_Weigh_mirror_bit_exact_mask(case):
+    """functional.backproject_Weigh on the reference's own hypotheses: per-view
+    valid mask bit-exact, per-view volume within tolerance, gradients too."""
+    from mvsdet_b200 import functional as F_
+    scene, gold = load_golden(case)
+    cfg = scene["cfg"]
+    h, w = cfg.crop_hw
+    v = cfg.n_views
+    feat = scene["feature"][:, :, :h, :w].clone().requires_grad_(True)
+    est_depth = torch.from_numpy(gold["est_depth"])[:, :, :h, :w]
+    est_dens = torch.from_numpy(gold["est_densities"])[:, :, :h, :w].clone().requires_grad_(True)
+    depth_r = est_depth.reshape(v, cfg.topk, -1).transpose(2, 1).unsqueeze(2)
+    dens_r = est_dens.reshape(v, cfg.topk, -1).transpose(2, 1).unsqueeze(2)
+    points = torch.from_numpy(gold["points"])
+    projection = torch.from_numpy(gold["projection"])
+    want_vol, want_valid = O.backproject_weigh(feat, points, projection, depth_r,
+                                               cfg.voxel_size, dens_r)
+    assert np.array_equal(want_valid.numpy(), gold["valid"])
+    g = torch.randn(want_vol.shape, generator=torch.Generator().manual_seed(9))
+    gf_w, gd_w = torch.autograd.grad(want_vol, (feat, est_dens), g)
+
+    feat_c = scene["feature"].cuda()[:, :, :h, :w].clone().requires_grad_(True)
+    dens_c = est_dens.detach().cuda().requires_grad_(True)
+    depth_rc = est_depth.cuda().reshape(v, cfg.topk, -1).transpose(2, 1).unsqueeze(2)
+    dens_rc = dens_c.reshape(v, cfg.topk, -1).transpose(2, 1).unsqueeze(2)
+    vol, valid, gap, rmse = F_.backproject_Weigh(feat_c, points.cuda(), projection.cuda(), depth_rc,
+                                                 list(cfg.voxel_size), dens_rc)
+    assert float(gap) == 1.0 and float(rmse) == 1.0          # mvsdet.py:1489-1491
+    assert valid.dtype == torch.bool
+    assert np.array_equal(valid.cpu().numpy(), gold["valid"]), "valid mask not bit-exact"
+    _close(vol, want_vol, f"{case}:per-view volume")
+    gf, gd = torch.autograd.grad(vol, (feat_c, dens_c), g.cuda())
+    _close(gf, gf_w, f"{case}:g_features")
+    _close(gd, gd_w, f"{case}:g_prob")
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES[:2])
+def test_sample_depth_prob_and_avg_depth_mirrors(case):
+    from mvsdet_b200 import functional as F_
+    scene, gold = load_golden(case)
+    cfg = scene["cfg"]
+    prob = torch.from_numpy(gold["prob_volume"]).cuda()
+    off = torch.from_numpy(gold["off_pred"]).cuda()
+    d, p = F_.sample_depth_prob(prob, off, cfg.topk, near=cfg.near_far_range[0],
+                                depth_interval=cfg.depth_interval)
+    _close(d, gold["est_depth"], "est_depth")
+    _close(p, gold["est_densities"], "est_densities", rtol=0, atol_scale=0)   # pure selection
+    avg = F_.compute_avg_depth(prob, off, near=cfg.near_far_range[0],
+                               depth_interval=cfg.depth_interval)
+    h, w = cfg.crop_hw
+    _close(avg[:, :h, :w].unsqueeze(1), gold["depth_coding"], "depth_coding")
+
+
+def test_pack_unpack_roundtrip():
+    from mvsdet_b200 import _lib, ops
+    x = torch.randn(3, 20, 7, 9, device="cuda")
+    cl = ops.pack_features(x, torch.float32)
+    assert cl.permute(0, 2, 3, 1).is_contiguous()
+    assert torch.equal(cl, x)
+    bf = ops.pack_features(x, torch.bfloat16)
+    assert torch.equal(bf, x.to(torch.bfloat16))
+    out = torch.empty_like(x)
+    _lib.call("mvsd_unpack_nhwc_to_nchw", cl.data_ptr(), out.data_ptr(), 0, 3, 20, 7, 9,
+              torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(out, x)
+
+
+def test_errors_are_loud():
+    from mvsdet_b200 import ops
+    with pytest.raises(ValueError):
+        ops.pack_features(torch.randn(1, 4, 4, 4))            # CPU tensor: no CPU path
+    x = torch.randn(2, 6, 4, 4, device="cuda")                # C not a multiple of 4
+    cl = x.contiguous(memory_format=torch.channels_last)
+    nbr = torch.tensor([[1], [0]], dtype=torch.int32, device="cuda")
+    hom = torch.zeros(2, 1, 12, device="cuda")
+    dv = torch.ones(2, 4, device="cuda")
+    with pytest.raises(ValueError):
+        ops.plane_sweep_variance(cl, nbr, hom, dv)
+    with pytest.raises(ValueError):
+        ops.plane_sweep_variance(x, nbr, hom, dv)             # not channels_last
+
+
+def test_single_view_scene_variance_is_zero():
+    """V=1 -> k = min(2, V-1) = 0 (mvsdet.py:432): S2/1 - (S1/1)^2 == 0."""
+    from mvsdet_b200 import ops
+    x = torch.randn(1, 8, 5, 6, device="cuda").contiguous(memory_format=torch.channels_last)
+    nbr = torch.zeros(1, 0, dtype=torch.int32, device="cuda")
+    hom = torch.zeros(1, 0, 12, device="cuda")
+    dv = torch.linspace(0.2, 4.6, 12, device="cuda").unsqueeze(0)
+    var = ops.plane_sweep_variance(x, nbr, hom, dv)
+    assert tuple(var.shape) == (1, 8, 12, 5, 6)
+    assert float(var.abs().max()) == 0.0
