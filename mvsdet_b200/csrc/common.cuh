@@ -87,8 +87,10 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float4 v) {
 // is outside.
 struct alignas(16) WarpSample {
   float w00, w01, w10, w11;     // (y0,x0) (y0,x0+1) (y0+1,x0) (y0+1,x0+1)
-  int p00, p01, p10, p11;       // pixel indices, valid even when weight is 0
+  unsigned p00, p01, p10, p11;  // tap offsets (y*W+x)*scale, valid even when the
+                                // weight is 0; p00 == kNoSample <=> no tap at all
 };
+constexpr unsigned kNoSample = 0xffffffffu;
 
 // Follows mvs_models/module.py:120-142 op by op:
 //   q = (rot @ (x,y,1)) * depth + trans          matmul = FMA chain over k
@@ -99,7 +101,7 @@ struct alignas(16) WarpSample {
 // ops), hence the explicit _rn intrinsics: no FMA contraction here.
 __device__ __forceinline__ WarpSample make_warp_sample(const float* __restrict__ m,
                                                        float x, float y, float depth,
-                                                       int H, int W) {
+                                                       int H, int W, int scale) {
   float rx = fmaf(m[2], 1.0f, fmaf(m[1], y, __fmul_rn(m[0], x)));
   float ry = fmaf(m[5], 1.0f, fmaf(m[4], y, __fmul_rn(m[3], x)));
   float rz = fmaf(m[8], 1.0f, fmaf(m[7], y, __fmul_rn(m[6], x)));
@@ -119,7 +121,7 @@ __device__ __forceinline__ WarpSample make_warp_sample(const float* __restrict__
   bool iny = (y0f >= -1.0f) && (y0f <= (float)(H - 1));
   if (!(inx && iny)) {
     s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
-    s.p00 = s.p01 = s.p10 = s.p11 = -1;
+    s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
     return s;
   }
   int x0 = (int)x0f, y0 = (int)y0f;
@@ -133,10 +135,10 @@ __device__ __forceinline__ WarpSample make_warp_sample(const float* __restrict__
   s.w01 = (vx1 && vy0) ? __fmul_rn(ey, wx) : 0.f;
   s.w10 = (vx0 && vy1) ? __fmul_rn(wy, ex) : 0.f;
   s.w11 = (vx1 && vy1) ? __fmul_rn(wy, wx) : 0.f;
-  s.p00 = cy0 * W + cx0;
-  s.p01 = cy0 * W + cx1;
-  s.p10 = cy1 * W + cx0;
-  s.p11 = cy1 * W + cx1;
+  s.p00 = (unsigned)((cy0 * W + cx0) * scale);
+  s.p01 = (unsigned)((cy0 * W + cx1) * scale);
+  s.p10 = (unsigned)((cy1 * W + cx0) * scale);
+  s.p11 = (unsigned)((cy1 * W + cx1) * scale);
   return s;
 }
 

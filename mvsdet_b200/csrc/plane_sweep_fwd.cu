@@ -1,0 +1,207 @@
+// Plane-sweep variance volume, forward (and the stand-alone homography warp).
+// See plane_sweep.cuh for the design; mvsdet.py:439-467, module.py:105-146.
+#include "plane_sweep.cuh"
+
+namespace mvsd {
+
+#ifndef MVSD_FWD_MINB
+#define MVSD_FWD_MINB 1
+#endif
+template <typename TIn, typename TOut, int KMAX, int G, bool FULL, bool WARP_ONLY>
+__global__ void __launch_bounds__(kSweepThreads, MVSD_FWD_MINB) sweep_fwd_kernel(const SweepParams p) {
+  __shared__ WarpSample s_tab[kRows][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const SweepCoord c = sweep_coord<G>(p, warp, lane);
+  if (c.y >= p.H) return;                       // warps are independent: no CTA barrier below
+  const int C = p.C, k = p.k, HW = p.H * p.W;
+  const TIn* feat = static_cast<const TIn*>(p.feat);
+  const TIn* ref_row = feat + ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+  TOut* out_row = static_cast<TOut*>(p.out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+  const TIn* nsrc[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    int n = c.v + p.ref_begin;
+    if (!WARP_ONLY && j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
+    nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+  }
+  const float inv_n = 1.0f / (float)(k + 1);
+  const int spp = kRun * k;
+  const int ppf = k > 0 ? max(1, 32 / spp) : p.D;      // planes per geometry pass
+
+  for (int d0 = 0; d0 < p.D; d0 += ppf) {
+    if (k > 0) {
+      __syncwarp();
+      fill_samples(s_tab[warp], p, c, d0, ppf, lane);
+      __syncwarp();
+    }
+    const int dend = min(p.D, d0 + ppf);
+    for (int d = d0; d < dend; ++d) {
+      float4 col[KMAX][2][2][G];
+      unsigned id_top[KMAX], id_bot[KMAX];
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        id_top[j] = id_bot[j] = kNoTap;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          col[j][0][0][g] = col[j][0][1][g] = col[j][1][0][g] = col[j][1][1][g] = f4zero();
+      }
+      const WarpSample* tab = s_tab[warp] + (d - d0) * spp;
+      TOut* out_d = out_row + (size_t)d * HW * C;
+#pragma unroll
+      for (int i = 0; i < kRun; ++i) {
+        if (i >= c.npix) break;
+        float4 s1[G], s2[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          s1[g] = f4zero();
+          if (!WARP_ONLY && group_on<FULL>(c.c0, g, C)) s1[g] = Io<TIn>::ld(ref_row + i * C + 128 * g);
+          s2[g] = f4mul(s1[g], s1[g]);
+        }
+        if (p.pf > 0) {
+          const int ahead = (d - d0) * spp + (i + p.pf) * k;
+          if (ahead + k <= ppf * spp) {
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j)
+              if (j < k) prefetch_sample<TIn, G, FULL>(nsrc[j], s_tab[warp] + ahead + j, c.c0, C);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          if (j >= k) break;
+          const WarpSample s = tab[i * k + j];
+          if (s.p00 == kNoSample) {                // all four taps outside: adds 0
+            id_top[j] = id_bot[j] = kNoTap;
+            continue;
+          }
+          float4 wv[G];
+          gather_taps<TIn, G, FULL, true>(nsrc[j], s, c.c0, C, col[j], id_top[j], id_bot[j], i, wv);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            s1[g] = f4add(s1[g], wv[g]);
+            s2[g] = f4fma(wv[g], wv[g], s2[g]);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (!group_on<FULL>(c.c0, g, C)) continue;
+          float4 r;
+          if (WARP_ONLY) {
+            r = s1[g];
+          } else {
+            // var = S2/n - (S1/n)^2 (mvsdet.py:467); "/n" as "*(1/n)", which is
+            // what ATen's CUDA division by a scalar does
+            const float4 m = f4scale(s1[g], inv_n);
+            // (no FMA contraction: S2/n and (S1/n)^2 are rounded separately in
+            // the reference, which makes the variance of k = 0 exactly 0)
+            r.x = __fsub_rn(s2[g].x * inv_n, __fmul_rn(m.x, m.x));
+            r.y = __fsub_rn(s2[g].y * inv_n, __fmul_rn(m.y, m.y));
+            r.z = __fsub_rn(s2[g].z * inv_n, __fmul_rn(m.z, m.z));
+            r.w = __fsub_rn(s2[g].w * inv_n, __fmul_rn(m.w, m.w));
+          }
+          Io<TOut>::st_stream(out_d + i * C + 128 * g, r);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+int sweep_check(const char* who, int V, int C, int D, int H, int W, int k, int layout) {
+  if (V <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || k < 0)
+    return fail(MVSD_ERR_INVALID_ARG, "%s: non-positive dimension", who);
+  if (C % 4 != 0 || C > MVSD_MAX_C)
+    return fail(MVSD_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 4 and <= %d", who, C, MVSD_MAX_C);
+  if (k > MVSD_MAX_K) return fail(MVSD_ERR_UNSUPPORTED, "%s: k=%d > %d", who, k, MVSD_MAX_K);
+  if ((long long)H * W * C >= (1LL << 31))
+    return fail(MVSD_ERR_UNSUPPORTED, "%s: one feature map must stay below 2^31 elements", who);
+  if (layout != MVSD_CHANNELS_LAST)
+    return fail(MVSD_ERR_UNSUPPORTED, "%s: only MVSD_CHANNELS_LAST volumes are implemented", who);
+  return MVSD_OK;
+}
+
+// channel groups (of 128) per warp: 2 keeps all 256 FPN channels of a tap in one
+// warp (fewest instructions per byte); tuning key 3 overrides (1, 2).
+int sweep_groups(int C) {
+  const int t = tuning(3);
+  if (t == 1 || t == 2) return t;
+  return C > 128 ? 2 : 1;
+}
+
+bool sweep_grid(SweepParams& p, int G, dim3& grid) {
+  p.runs_x = (p.W + kRun - 1) / kRun;
+  p.tiles_y = (p.H + kRows - 1) / kRows;
+  p.slices = (p.C + 128 * G - 1) / (128 * G);
+  p.pf = tuning(4) > 0 ? tuning(4) - 1 : 2;          // key 4: 1 = off, n+1 = distance n
+  const long long blocks = (long long)p.V * p.slices * p.tiles_y * p.runs_x;
+  if (blocks > 2147483647LL) return false;
+  grid = dim3((unsigned)blocks);
+  return true;
+}
+
+template <typename TIn, typename TOut, bool WARP_ONLY>
+static int launch_fwd_k(SweepParams& p, cudaStream_t st) {
+  dim3 grid;
+  const int G = sweep_groups(p.C);
+  if (!sweep_grid(p, G, grid)) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_fwd: grid too large");
+  const bool full = p.C % (128 * G) == 0;
+  const int kmax = WARP_ONLY ? 1 : (p.k <= 1 ? 1 : (p.k == 2 ? 2 : 4));
+#define MVSD_FWD(KM, GG, FU) \
+  sweep_fwd_kernel<TIn, TOut, KM, GG, FU, WARP_ONLY><<<grid, kSweepThreads, 0, st>>>(p)
+#define MVSD_FWD_G(KM)                                                   \
+  do {                                                                   \
+    if (G == 2) { if (full) MVSD_FWD(KM, 2, true); else MVSD_FWD(KM, 2, false); } \
+    else { if (full) MVSD_FWD(KM, 1, true); else MVSD_FWD(KM, 1, false); }        \
+  } while (0)
+  if (kmax == 1) MVSD_FWD_G(1);
+  else if (kmax == 2) MVSD_FWD_G(2);
+  else MVSD_FWD_G(4);
+#undef MVSD_FWD_G
+#undef MVSD_FWD
+  count_launch();
+  return check_launch("plane_sweep_fwd");
+}
+
+template <bool WARP_ONLY>
+static int launch_fwd(SweepParams& p, int in_dtype, int out_dtype, cudaStream_t st) {
+  if (in_dtype == MVSD_F32 && out_dtype == MVSD_F32) return launch_fwd_k<float, float, WARP_ONLY>(p, st);
+  if (in_dtype == MVSD_BF16 && out_dtype == MVSD_F32)
+    return launch_fwd_k<__nv_bfloat16, float, WARP_ONLY>(p, st);
+  if (in_dtype == MVSD_BF16 && out_dtype == MVSD_BF16)
+    return launch_fwd_k<__nv_bfloat16, __nv_bfloat16, WARP_ONLY>(p, st);
+  if (in_dtype == MVSD_F32 && out_dtype == MVSD_BF16)
+    return launch_fwd_k<float, __nv_bfloat16, WARP_ONLY>(p, st);
+  return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_fwd: bad dtype");
+}
+
+}  // namespace mvsd
+
+using namespace mvsd;
+
+extern "C" int mvsd_plane_sweep_fwd(const void* feat, int feat_dtype, const int32_t* nbr_ids,
+                                    const float* hom, const float* depth_values, void* out,
+                                    int out_dtype, int out_layout, int V, int C, int D, int H,
+                                    int W, int k, int ref_begin, void* stream) {
+  if (int e = sweep_check("plane_sweep_fwd", V, C, D, H, W, k, out_layout)) return e;
+  if (!feat || !out || !depth_values || (k > 0 && (!nbr_ids || !hom)))
+    return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_fwd: null pointer");
+  if (ref_begin < 0) return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_fwd: negative ref_begin");
+  SweepParams p{};
+  p.feat = feat; p.nbr = nbr_ids; p.hom = hom; p.depth = depth_values; p.out = out;
+  p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin;
+  return launch_fwd<false>(p, feat_dtype, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mvsd_homo_warp_fwd(const void* src, int src_dtype, const float* hom,
+                                  const float* depth_values, void* out, int out_dtype,
+                                  int out_layout, int B, int C, int D, int H, int W,
+                                  void* stream) {
+  if (int e = sweep_check("homo_warp_fwd", B, C, D, H, W, 1, out_layout)) return e;
+  if (!src || !hom || !depth_values || !out)
+    return fail(MVSD_ERR_INVALID_ARG, "homo_warp_fwd: null pointer");
+  SweepParams p{};
+  p.feat = src; p.nbr = nullptr; p.hom = hom; p.depth = depth_values; p.out = out;
+  p.V = B; p.C = C; p.D = D; p.H = H; p.W = W; p.k = 1; p.ref_begin = 0;
+  return launch_fwd<true>(p, src_dtype, out_dtype, static_cast<cudaStream_t>(stream));
+}

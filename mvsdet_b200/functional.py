@@ -41,7 +41,11 @@ def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.
         raise ValueError("per-pixel depth_values [B,D,H,W] (module.py:130-133) is not used by "
                          "MVSDet and not implemented")
     with torch.no_grad():
-        hom = G.homography_params(src_proj.float(), ref_proj.float()).to(src_fea.device)
+        # 4x4 algebra on the host in fp32 (LAPACK), like the per-scene geometry
+        # block: bit-identical to the CPU reference; cuSOLVER's batched inverse
+        # differs in the last bits, which moves sample positions by ~1e-5 px.
+        hom = G.homography_params(src_proj.detach().float().cpu(),
+                                  ref_proj.detach().float().cpu()).to(src_fea.device)
     feat = ops.pack_features(src_fea, src_fea.dtype if src_fea.dtype == torch.bfloat16 else torch.float32)
     return ops.homo_warp(feat, hom, depth_values.to(src_fea.device).float(),
                          out_dtype=torch.float32)
@@ -58,14 +62,14 @@ def sample_depth_prob(prob_volume: torch.Tensor, off_pred: torch.Tensor, topk: i
     """prob_volume, off_pred [V,D,H,W] (already softmax-ed / sigmoid-ed) ->
     (est_depth, est_density) each [V,topk,H,W]."""
     res = ops.topk_hypotheses(_stack_prob_off(prob_volume, off_pred), near, depth_interval, topk)
-    return res[0], res[1]
+    return res[2], res[3]
 
 
 def compute_avg_depth(prob_volume: torch.Tensor, off_pred: torch.Tensor, *, near: float,
                       depth_interval: float) -> torch.Tensor:
     """Depth expectation [V,H,W] = sum_d p_d (d*interval + near + off_d*interval)."""
     res = ops.topk_hypotheses(_stack_prob_off(prob_volume, off_pred), near, depth_interval, 1)
-    return res[3]
+    return res[5]
 
 
 def backproject_Weigh(features, points, projection, depth, voxel_size, prob, gt_depth=None,

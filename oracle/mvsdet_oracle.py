@@ -198,24 +198,30 @@ def depth_values_for(near_far_range: Sequence[float], num_depth: int) -> np.ndar
 
 
 def plane_sweep_variance(feature, w2c, feat_intrinsic, neighbor_ids, depth_values,
-                         training: bool = True):
+                         training: bool = True, view_subset: Optional[int] = None):
     """[V,C,Hf,Wf] -> variance volume [V,C,D,Hf,Wf] (mvsdet.py:439-467).
 
     S1 = ref + sum_j warped_j, S2 = ref^2 + sum_j warped_j^2 with the
     reference view broadcast over D; var = S2/(k+1) - (S1/(k+1))^2, in exactly
     that order.  ``training`` selects the out-of-place branch (:458-459,
     autograd-safe) or the in-place eval branch (:463-464); the values are the
-    same.
+    same.  ``view_subset`` = n sweeps only the first n reference views (their
+    neighbours are still drawn from all views): the bounded CPU-baseline sample
+    of bench.py, not a reference feature.
     """
-    v = feature.shape[0]
+    v = feature.shape[0] if view_subset is None else int(view_subset)
     k = neighbor_ids.shape[1]
     d = depth_values.shape[-1]
-    ref_volume = feature.unsqueeze(2).repeat(1, 1, d, 1, 1)
+    neighbor_ids = neighbor_ids[:v]
+    ref_volume = feature[:v].unsqueeze(2).repeat(1, 1, d, 1, 1)
     volume_sum = ref_volume
     volume_sq_sum = ref_volume ** 2
     del ref_volume
     nei_features = feature[neighbor_ids.reshape(-1)].view(v, k, *feature.shape[1:])
-    ref_proj, nei_projs = collect_proj(w2c, feat_intrinsic, neighbor_ids)
+    all_proj = torch.matmul(feat_intrinsic if feat_intrinsic.dim() == 3
+                            else feat_intrinsic.unsqueeze(0).repeat(w2c.shape[0], 1, 1), w2c)
+    ref_proj = all_proj[:v]
+    nei_projs = torch.unbind(all_proj[neighbor_ids.reshape(-1)].view(v, k, 4, 4), dim=1)
     if depth_values.dim() == 1:
         depth_values = depth_values.unsqueeze(0).repeat(v, 1)
     for j in range(k):
@@ -366,7 +372,8 @@ def aggregate_views(volume, valid):
 # the inline glue of extract_feat -- mvsdet.py:404-515
 # --------------------------------------------------------------------------
 def hot_path(feature, img_meta, cost_regularization, *, near_far_range, num_depth,
-             topk, n_voxels, voxel_size, stride: int = 4, training: bool = True):
+             topk, n_voxels, voxel_size, stride: int = 4, training: bool = True,
+             view_subset: Optional[int] = None):
     """One scene through mvsdet.py:404-515 / :681-682.
 
     ``feature`` [V,C,Hf,Wf]; ``img_meta`` carries ``lidar2img`` {extrinsic,
@@ -392,7 +399,10 @@ def hot_path(feature, img_meta, cost_regularization, *, near_far_range, num_dept
     depth_interval = (near_far_range[1] - near_far_range[0]) / num_depth
     dvals = torch.as_tensor(depth_values_for(near_far_range, num_depth))
     variance = plane_sweep_variance(feature, w2c, k_feat, neighbor_ids, dvals,
-                                    training=training)
+                                    training=training, view_subset=view_subset)
+    if view_subset is not None:            # bounded CPU-baseline sample (bench.py)
+        v = int(view_subset)
+        projection = projection[:v]
     cost_out = cost_regularization(variance)
     prob_volume, off_pred = depth_probability(cost_out)
     est_depth, est_dens, est_idx = sample_depth_prob(
@@ -403,7 +413,7 @@ def hot_path(feature, img_meta, cost_regularization, *, near_far_range, num_dept
                                      depth_interval)[:, :height, :width].unsqueeze(1)
     depth_r = est_depth_c.reshape(v, topk, -1).transpose(2, 1).unsqueeze(2)
     dens_r = est_dens_c.reshape(v, topk, -1).transpose(2, 1).unsqueeze(2)
-    volume, valid = backproject_weigh(feature[:, :, :height, :width], points,
+    volume, valid = backproject_weigh(feature[:v, :, :height, :width], points,
                                       projection, depth_r, voxel_size, dens_r)
     volume_mean, count = aggregate_views(volume, valid)
     return dict(neighbor_ids=neighbor_ids, variance=variance, cost_out=cost_out,

@@ -20,12 +20,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-def _close(a, b, what, rtol=RTOL, atol_scale=1e-4):
+def _close(a, b, what, rtol=RTOL, atol_scale=1e-4, abs_floor=0.0):
     a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a)).double()
     b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b)).double()
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     rms = float(b.pow(2).mean().sqrt()) if b.numel() else 0.0
-    tol = atol_scale * max(rms, 1e-30) + rtol * b.abs()
+    tol = max(atol_scale * rms, abs_floor, 1e-30) + rtol * b.abs()
     err = (a - b).abs()
     bad = err > tol
     assert not bool(bad.any()), (
@@ -70,8 +70,12 @@ def test_chain_fp32_vs_reference_golden(case, channels_first):
     for key in ("variance", "prob_volume", "off_pred", "est_depth", "est_densities",
                 "depth_coding", "volume_mean"):
         _close(res[key], gold[key], f"{case}:{key}")
-    for key in ("g_feature_from_variance", "g_feature_from_voxels", "g_cost_out"):
+    for key in ("g_feature_from_variance", "g_feature_from_voxels"):
         _close(res[key], gold[key], f"{case}:{key}")
+    # with T == 1 the normalised probability is identically 1 and its gradient
+    # cancels to rounding noise of terms of magnitude ~|g|*|f|*sqrt(C) ~ 10:
+    # judge against that scale (1e-6 relative to it), not against ~0.
+    _close(res["g_cost_out"], gold["g_cost_out"], f"{case}:g_cost_out", abs_floor=1e-5)
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES[:2])
@@ -154,7 +158,7 @@ def test_backproject_Weigh_mirror_bit_exact_mask(case):
     _close(vol, want_vol, f"{case}:per-view volume")
     gf, gd = torch.autograd.grad(vol, (feat_c, dens_c), g.cuda())
     _close(gf, gf_w, f"{case}:g_features")
-    _close(gd, gd_w, f"{case}:g_prob")
+    _close(gd, gd_w, f"{case}:g_prob", abs_floor=1e-5)      # T == 1: cancels to noise
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES[:2])
