@@ -1,72 +1,44 @@
 // Plane-sweep variance volume, backward (and the homography warp's backward).
 // See plane_sweep.cuh for the design.  What autograd computes through
 // mvsdet.py:439-467, with n = k+1, mu = S1/n:
-//   dL/dref       += sum_d G (2/n) (ref - mu_d)
-//   dL/dwarped_j   = G (2/n) (warped_j - mu)   -> bilinear scatter into neighbour j
-// The scatter uses fp32 vector REDs (the L2 atomic unit is the binding
-// resource: 32 B / clk / slice); along a run the contributions to a tap column
-// shared by two consecutive pixels are summed in registers first, so a source
-// pixel receives one RED per run instead of two.
+//   dL/dref       += sum_d G (2/n) (ref - mu_d)        (registers, one RED at the end)
+//   dL/dwarped_j   = G (2/n) (warped_j - mu)            -> bilinear scatter into neighbour j
+// The scatter uses fp32 16-byte vector REDs (red.global.add.v4.f32); ncu shows
+// the L2 atomic unit (32 B / clk / slice) as the binding resource of this kernel.
 #include "plane_sweep.cuh"
 
 namespace mvsd {
 
 template <int G, bool FULL>
-__device__ __forceinline__ void red_group(float* dst, unsigned off, const float4 (&v)[G], int c0,
-                                          int C) {
+__device__ __forceinline__ void red_tap(float* dst, unsigned off, const float4 (&gw)[G], float w,
+                                        int c0, int C) {
+  if (w == 0.f) return;                         // clamped (outside) tap: contributes nothing
   float* a = at(dst, off);
 #pragma unroll
   for (int g = 0; g < G; ++g)
-    if (group_on<FULL>(c0, g, C)) red_add_f32x4(a + 128 * g, v[g]);
+    if (group_on<FULL>(c0, g, C)) red_add_f32x4(a + 128 * g, f4scale(gw[g], w));
 }
 
-template <int G, bool FULL>
-__device__ __forceinline__ void flush_open(float* dst, unsigned& id, const float4 (&acc)[G], int c0,
-                                           int C) {
-  if (id != kNoTap) red_group<G, FULL>(dst, id, acc, c0, C);
-  id = kNoTap;
-}
-
-// One side (top or bottom row) of the scatter of one sample: the left tap
-// merges with the pending right tap of the previous pixel when it is the same
-// source pixel and leaves as one RED; the right tap stays pending.
-template <int G, bool FULL>
-__device__ __forceinline__ void scatter_side(float* dst, const float4 (&gw)[G], float w_left,
-                                             float w_right, unsigned p_left, unsigned p_right,
-                                             unsigned& open_id, float4 (&open)[G], int c0, int C) {
-  float4 a[G];
-  if (open_id == p_left) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) a[g] = f4fma(gw[g], w_left, open[g]);
-    red_group<G, FULL>(dst, p_left, a, c0, C);
-  } else {
-    flush_open<G, FULL>(dst, open_id, open, c0, C);
-    if (w_left != 0.f) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) a[g] = f4scale(gw[g], w_left);
-      red_group<G, FULL>(dst, p_left, a, c0, C);
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < G; ++g) open[g] = f4scale(gw[g], w_right);
-  open_id = w_right != 0.f ? p_right : kNoTap;
-}
-
-#ifndef MVSD_BWD_MINB
-#define MVSD_BWD_MINB 1
-#endif
 template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool WARP_ONLY>
-__global__ void __launch_bounds__(kSweepThreads, MVSD_BWD_MINB) sweep_bwd_kernel(const SweepParams p) {
-  __shared__ WarpSample s_tab[kRows][32];
-  __shared__ float4 s_gref[WARP_ONLY ? 1 : kRows][WARP_ONLY ? 1 : kRun][G][32];
+__global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepParams p) {
+  __shared__ WarpSample s_tab[kSweepWarps][kSlots];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
-  if (c.y >= p.H) return;
+  if (!c.ok) return;
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
-  const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
-  const TIn* ref_row = feat + ref_off;
-  const TG* g_row = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+  const unsigned pix = (unsigned)(c.y * p.W + c.x);
+  const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + pix) * C + c.c0;
+  const TG* g_pix = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + pix) * C + c.c0;
+  const size_t plane_stride = (size_t)HW * C;
+
+  float4 ref[G], gref[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    ref[g] = f4zero();
+    gref[g] = f4zero();
+    if (!WARP_ONLY && group_on<FULL>(c.c0, g, C)) ref[g] = Io<TIn>::ld(feat + ref_off + 128 * g);
+  }
   const TIn* nsrc[KMAX];
   float* ndst[KMAX];
 #pragma unroll
@@ -78,102 +50,65 @@ __global__ void __launch_bounds__(kSweepThreads, MVSD_BWD_MINB) sweep_bwd_kernel
   }
   const float inv_n = 1.0f / (float)(k + 1);
   const float two_inv_n = 2.0f * inv_n;
-  const int spp = kRun * k;
-  const int ppf = k > 0 ? max(1, 32 / spp) : p.D;
+  const int dc = k > 0 ? kSlots / k : p.D;
 
-  if (!WARP_ONLY) {
-#pragma unroll
-    for (int i = 0; i < kRun; ++i)
-#pragma unroll
-      for (int g = 0; g < G; ++g) s_gref[warp][i][g][lane] = f4zero();
-  }
-
-  for (int d0 = 0; d0 < p.D; d0 += ppf) {
+  for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, ppf, lane);
+      fill_samples(s_tab[warp], p, c, d0, dc, lane);
       __syncwarp();
     }
-    const int dend = min(p.D, d0 + ppf);
+    const int dend = min(p.D, d0 + dc);
     for (int d = d0; d < dend; ++d) {
-      float4 open_top[KMAX][G], open_bot[KMAX][G];   // pending right-column contributions
-      unsigned o_top[KMAX], o_bot[KMAX];
+      const TG* gp = g_pix + (size_t)d * plane_stride;
+      float4 gv[G], mu[G];
+      float4 wv[KMAX][G];
+      WarpSample smp[KMAX];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        gv[g] = group_on<FULL>(c.c0, g, C) ? Io<TG>::ld_stream(gp + 128 * g) : f4zero();
+        mu[g] = ref[g];
+      }
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
-        o_top[j] = o_bot[j] = kNoTap;
 #pragma unroll
-        for (int g = 0; g < G; ++g) open_top[j][g] = open_bot[j][g] = f4zero();
+        for (int g = 0; g < G; ++g) wv[j][g] = f4zero();
+        if (j >= k) continue;
+        smp[j] = s_tab[warp][(d - d0) * k + j];
+        if (WARP_ONLY || smp[j].p00 == kNoSample) continue;
+        gather_taps<TIn, G, FULL>(nsrc[j], smp[j], c.c0, C, wv[j]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) mu[g] = f4add(mu[g], wv[j][g]);
       }
-      const WarpSample* tab = s_tab[warp] + (d - d0) * spp;
-      const TG* g_d = g_row + (size_t)d * HW * C;
-#pragma unroll
-      for (int i = 0; i < kRun; ++i) {
-        if (i >= c.npix) break;
-        float4 gv[G], ref[G], mu[G];
-        float4 wv[KMAX][G];
-        WarpSample smp[KMAX];
+      if (!WARP_ONLY) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const bool on = group_on<FULL>(c.c0, g, C);
-          gv[g] = on ? Io<TG>::ld_stream(g_d + i * C + 128 * g) : f4zero();
-          ref[g] = (!WARP_ONLY && on) ? Io<TIn>::ld(ref_row + i * C + 128 * g) : f4zero();
-          mu[g] = ref[g];
-        }
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-#pragma unroll
-          for (int g = 0; g < G; ++g) wv[j][g] = f4zero();
-          if (j >= k) continue;
-          smp[j] = tab[i * k + j];
-          if (WARP_ONLY || smp[j].p00 == kNoSample) continue;
-          float4 col[2][2][G];
-          unsigned t0 = kNoTap, t1 = kNoTap;
-          gather_taps<TIn, G, FULL, false>(nsrc[j], smp[j], c.c0, C, col, t0, t1, i, wv[j]);
-#pragma unroll
-          for (int g = 0; g < G; ++g) mu[g] = f4add(mu[g], wv[j][g]);
-        }
-        if (!WARP_ONLY) {
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            mu[g] = f4scale(mu[g], inv_n);
-            gv[g] = f4scale(gv[g], two_inv_n);
-            s_gref[warp][i][g][lane] = f4fma(gv[g], f4sub(ref[g], mu[g]), s_gref[warp][i][g][lane]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-          if (j >= k) continue;
-          const WarpSample s = smp[j];
-          if (s.p00 == kNoSample) {
-            flush_open<G, FULL>(ndst[j], o_top[j], open_top[j], c.c0, C);
-            flush_open<G, FULL>(ndst[j], o_bot[j], open_bot[j], c.c0, C);
-            continue;
-          }
-          float4 gw[G];
-#pragma unroll
-          for (int g = 0; g < G; ++g)
-            gw[g] = WARP_ONLY ? gv[g] : f4mul(gv[g], f4sub(wv[j][g], mu[g]));
-          scatter_side<G, FULL>(ndst[j], gw, s.w00, s.w01, s.p00, s.p01, o_top[j], open_top[j], c.c0, C);
-          scatter_side<G, FULL>(ndst[j], gw, s.w10, s.w11, s.p10, s.p11, o_bot[j], open_bot[j], c.c0, C);
+          mu[g] = f4scale(mu[g], inv_n);
+          gv[g] = f4scale(gv[g], two_inv_n);
+          gref[g] = f4fma(gv[g], f4sub(ref[g], mu[g]), gref[g]);
         }
       }
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
         if (j >= k) continue;
-        flush_open<G, FULL>(ndst[j], o_top[j], open_top[j], c.c0, C);
-        flush_open<G, FULL>(ndst[j], o_bot[j], open_bot[j], c.c0, C);
+        const WarpSample s = smp[j];
+        if (s.p00 == kNoSample) continue;
+        float4 gw[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          gw[g] = WARP_ONLY ? gv[g] : f4mul(gv[g], f4sub(wv[j][g], mu[g]));
+        red_tap<G, FULL>(ndst[j], s.p00, gw, s.w00, c.c0, C);
+        red_tap<G, FULL>(ndst[j], s.p01, gw, s.w01, c.c0, C);
+        red_tap<G, FULL>(ndst[j], s.p10, gw, s.w10, c.c0, C);
+        red_tap<G, FULL>(ndst[j], s.p11, gw, s.w11, c.c0, C);
       }
     }
   }
   if (!WARP_ONLY) {
     float* dst = p.g_feat + ref_off;
 #pragma unroll
-    for (int i = 0; i < kRun; ++i) {
-      if (i >= c.npix) break;
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-        if (group_on<FULL>(c.c0, g, C)) red_add_f32x4(dst + i * C + 128 * g, s_gref[warp][i][g][lane]);
-    }
+    for (int g = 0; g < G; ++g)
+      if (group_on<FULL>(c.c0, g, C)) red_add_f32x4(dst + 128 * g, gref[g]);
   }
 }
 
@@ -200,6 +135,8 @@ static int launch_bwd_k(SweepParams& p, cudaStream_t st) {
   return check_launch("plane_sweep_bwd");
 }
 
+int launch_bwd_run(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st);
+
 }  // namespace mvsd
 
 using namespace mvsd;
@@ -217,6 +154,8 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   p.g_feat = g_feat;
   p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tuning key 5: 0/unset = run-merging variant when applicable, 1 = pixel kernel
+  if ((k == 1 || k == 2) && tuning(5) != 1) return launch_bwd_run(p, feat_dtype, g_dtype, st);
   if (feat_dtype == MVSD_F32 && g_dtype == MVSD_F32) return launch_bwd_k<float, float, false>(p, st);
   if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_F32)
     return launch_bwd_k<__nv_bfloat16, float, false>(p, st);

@@ -4,19 +4,26 @@
 
 namespace mvsd {
 
-#ifndef MVSD_FWD_MINB
-#define MVSD_FWD_MINB 1
-#endif
 template <typename TIn, typename TOut, int KMAX, int G, bool FULL, bool WARP_ONLY>
-__global__ void __launch_bounds__(kSweepThreads, MVSD_FWD_MINB) sweep_fwd_kernel(const SweepParams p) {
-  __shared__ WarpSample s_tab[kRows][32];
+__global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepParams p) {
+  __shared__ WarpSample s_tab[kSweepWarps][kSlots];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
-  if (c.y >= p.H) return;                       // warps are independent: no CTA barrier below
+  if (!c.ok) return;                            // warps are independent: no CTA barrier below
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
-  const TIn* ref_row = feat + ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
-  TOut* out_row = static_cast<TOut*>(p.out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+  const unsigned pix = (unsigned)(c.y * p.W + c.x);
+  TOut* out_pix = static_cast<TOut*>(p.out) + ((size_t)c.v * p.D * HW + pix) * C + c.c0;
+  const size_t plane_stride = (size_t)HW * C;
+
+  float4 ref[G], ref2[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    ref[g] = f4zero();
+    if (!WARP_ONLY && group_on<FULL>(c.c0, g, C))
+      ref[g] = Io<TIn>::ld(feat + ((size_t)(c.v + p.ref_begin) * HW + pix) * C + c.c0 + 128 * g);
+    ref2[g] = f4mul(ref[g], ref[g]);
+  }
   const TIn* nsrc[KMAX];
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
@@ -25,81 +32,54 @@ __global__ void __launch_bounds__(kSweepThreads, MVSD_FWD_MINB) sweep_fwd_kernel
     nsrc[j] = feat + (size_t)n * HW * C + c.c0;
   }
   const float inv_n = 1.0f / (float)(k + 1);
-  const int spp = kRun * k;
-  const int ppf = k > 0 ? max(1, 32 / spp) : p.D;      // planes per geometry pass
+  const int dc = k > 0 ? kSlots / k : p.D;      // planes per geometry pass
 
-  for (int d0 = 0; d0 < p.D; d0 += ppf) {
+  for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, ppf, lane);
+      fill_samples(s_tab[warp], p, c, d0, dc, lane);
       __syncwarp();
     }
-    const int dend = min(p.D, d0 + ppf);
+    const int dend = min(p.D, d0 + dc);
     for (int d = d0; d < dend; ++d) {
-      float4 col[KMAX][2][2][G];
-      unsigned id_top[KMAX], id_bot[KMAX];
+      float4 s1[G], s2[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        s1[g] = ref[g];
+        s2[g] = ref2[g];
+      }
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
-        id_top[j] = id_bot[j] = kNoTap;
+        if (j >= k) break;
+        const WarpSample s = s_tab[warp][(d - d0) * k + j];
+        if (s.p00 == kNoSample) continue;       // all four taps outside: adds 0
+        float4 wv[G];
+        gather_taps<TIn, G, FULL>(nsrc[j], s, c.c0, C, wv);
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-          col[j][0][0][g] = col[j][0][1][g] = col[j][1][0][g] = col[j][1][1][g] = f4zero();
+        for (int g = 0; g < G; ++g) {
+          s1[g] = f4add(s1[g], wv[g]);
+          s2[g] = f4fma(wv[g], wv[g], s2[g]);
+        }
       }
-      const WarpSample* tab = s_tab[warp] + (d - d0) * spp;
-      TOut* out_d = out_row + (size_t)d * HW * C;
+      TOut* o = out_pix + (size_t)d * plane_stride;
 #pragma unroll
-      for (int i = 0; i < kRun; ++i) {
-        if (i >= c.npix) break;
-        float4 s1[G], s2[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          s1[g] = f4zero();
-          if (!WARP_ONLY && group_on<FULL>(c.c0, g, C)) s1[g] = Io<TIn>::ld(ref_row + i * C + 128 * g);
-          s2[g] = f4mul(s1[g], s1[g]);
+      for (int g = 0; g < G; ++g) {
+        if (!group_on<FULL>(c.c0, g, C)) continue;
+        float4 r;
+        if (WARP_ONLY) {
+          r = s1[g];
+        } else {
+          // var = S2/n - (S1/n)^2 (mvsdet.py:467); "/n" as "*(1/n)", which is what
+          // ATen's CUDA division by a scalar does.  S2/n and (S1/n)^2 are rounded
+          // separately as in the reference (no FMA contraction), which keeps the
+          // variance of a single view (k = 0) exactly 0.
+          const float4 m = f4scale(s1[g], inv_n);
+          r.x = __fsub_rn(s2[g].x * inv_n, __fmul_rn(m.x, m.x));
+          r.y = __fsub_rn(s2[g].y * inv_n, __fmul_rn(m.y, m.y));
+          r.z = __fsub_rn(s2[g].z * inv_n, __fmul_rn(m.z, m.z));
+          r.w = __fsub_rn(s2[g].w * inv_n, __fmul_rn(m.w, m.w));
         }
-        if (p.pf > 0) {
-          const int ahead = (d - d0) * spp + (i + p.pf) * k;
-          if (ahead + k <= ppf * spp) {
-#pragma unroll
-            for (int j = 0; j < KMAX; ++j)
-              if (j < k) prefetch_sample<TIn, G, FULL>(nsrc[j], s_tab[warp] + ahead + j, c.c0, C);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-          if (j >= k) break;
-          const WarpSample s = tab[i * k + j];
-          if (s.p00 == kNoSample) {                // all four taps outside: adds 0
-            id_top[j] = id_bot[j] = kNoTap;
-            continue;
-          }
-          float4 wv[G];
-          gather_taps<TIn, G, FULL, true>(nsrc[j], s, c.c0, C, col[j], id_top[j], id_bot[j], i, wv);
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            s1[g] = f4add(s1[g], wv[g]);
-            s2[g] = f4fma(wv[g], wv[g], s2[g]);
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          if (!group_on<FULL>(c.c0, g, C)) continue;
-          float4 r;
-          if (WARP_ONLY) {
-            r = s1[g];
-          } else {
-            // var = S2/n - (S1/n)^2 (mvsdet.py:467); "/n" as "*(1/n)", which is
-            // what ATen's CUDA division by a scalar does
-            const float4 m = f4scale(s1[g], inv_n);
-            // (no FMA contraction: S2/n and (S1/n)^2 are rounded separately in
-            // the reference, which makes the variance of k = 0 exactly 0)
-            r.x = __fsub_rn(s2[g].x * inv_n, __fmul_rn(m.x, m.x));
-            r.y = __fsub_rn(s2[g].y * inv_n, __fmul_rn(m.y, m.y));
-            r.z = __fsub_rn(s2[g].z * inv_n, __fmul_rn(m.z, m.z));
-            r.w = __fsub_rn(s2[g].w * inv_n, __fmul_rn(m.w, m.w));
-          }
-          Io<TOut>::st_stream(out_d + i * C + 128 * g, r);
-        }
+        Io<TOut>::st_stream(o + 128 * g, r);
       }
     }
   }
@@ -121,7 +101,7 @@ int sweep_check(const char* who, int V, int C, int D, int H, int W, int k, int l
   return MVSD_OK;
 }
 
-// channel groups (of 128) per warp: 2 keeps all 256 FPN channels of a tap in one
+// Channel groups (of 128) per warp: 2 keeps all 256 FPN channels of a tap in one
 // warp (fewest instructions per byte); tuning key 3 overrides (1, 2).
 int sweep_groups(int C) {
   const int t = tuning(3);
@@ -130,11 +110,10 @@ int sweep_groups(int C) {
 }
 
 bool sweep_grid(SweepParams& p, int G, dim3& grid) {
-  p.runs_x = (p.W + kRun - 1) / kRun;
-  p.tiles_y = (p.H + kRows - 1) / kRows;
+  p.tiles_x = (p.W + kPatchW - 1) / kPatchW;
+  p.tiles_y = (p.H + kPatchH - 1) / kPatchH;
   p.slices = (p.C + 128 * G - 1) / (128 * G);
-  p.pf = tuning(4) > 0 ? tuning(4) - 1 : 2;          // key 4: 1 = off, n+1 = distance n
-  const long long blocks = (long long)p.V * p.slices * p.tiles_y * p.runs_x;
+  const long long blocks = (long long)p.V * p.slices * p.tiles_y * p.tiles_x;
   if (blocks > 2147483647LL) return false;
   grid = dim3((unsigned)blocks);
   return true;
@@ -149,8 +128,8 @@ static int launch_fwd_k(SweepParams& p, cudaStream_t st) {
   const int kmax = WARP_ONLY ? 1 : (p.k <= 1 ? 1 : (p.k == 2 ? 2 : 4));
 #define MVSD_FWD(KM, GG, FU) \
   sweep_fwd_kernel<TIn, TOut, KM, GG, FU, WARP_ONLY><<<grid, kSweepThreads, 0, st>>>(p)
-#define MVSD_FWD_G(KM)                                                   \
-  do {                                                                   \
+#define MVSD_FWD_G(KM)                                                            \
+  do {                                                                            \
     if (G == 2) { if (full) MVSD_FWD(KM, 2, true); else MVSD_FWD(KM, 2, false); } \
     else { if (full) MVSD_FWD(KM, 1, true); else MVSD_FWD(KM, 1, false); }        \
   } while (0)
