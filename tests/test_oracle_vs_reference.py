@@ -1,0 +1,81 @@
+"""Pin the oracle against the LIVE reference (build container only).
+
+``oracle/ref_loader.py`` slices the reference's own functions out of
+/root/reference and executes them verbatim; here fresh seeded scenes -- not the
+ones frozen in tests/golden -- go through both the reference chain
+(tests/golden/make_golden.py: mvsdet.py:404-515 followed statement by statement)
+and ``oracle.hot_path``.  Skipped where the mount does not exist (the GPU box).
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, oracle_chain
+from mvsdet_b200.scene import make_scene, tiny_config
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(),
+                                reason="/root/reference is not mounted on this machine")
+
+CASES = [
+    (tiny_config(n_views=6, channels=8, num_depth=8), 101),
+    (tiny_config(n_views=3, channels=8, num_depth=4, topk=2, per_view_intrinsics=True,
+                 near_far_range=(0.5, 5.5)), 102),
+    (tiny_config(n_views=7, channels=4, num_depth=16, topk=3, n_voxels=(10, 8, 4)), 103),
+]
+
+
+def _make_golden_module():
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")
+    spec = importlib.util.spec_from_file_location("_make_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("cfg,seed", CASES)
+def test_oracle_equals_live_reference(ref, cfg, seed):
+    mg = _make_golden_module()
+    scene = make_scene(cfg, seed)
+    want = mg.reference_chain(ref, scene)
+    got = oracle_chain(scene)
+    for key in ("neighbor_ids", "est_idx", "valid", "count"):
+        assert np.array_equal(got[key].numpy(), want[key].numpy()), key
+    for key in ("variance", "prob_volume", "off_pred", "est_depth", "est_densities",
+                "depth_coding", "volume_mean", "projection", "points",
+                "g_feature_from_variance", "g_feature_from_voxels", "g_cost_out"):
+        assert_close(got[key], want[key], rtol=1e-6, atol=1e-6, what=key)
+
+
+def test_geometry_mirrors_equal_live_reference(ref):
+    """The product's host-side geometry (mvsdet_b200/geometry.py) against the
+    reference's knn / get_nearest_pose_ids / collect_proj / get_points /
+    _compute_projection on the same camera set."""
+    from mvsdet_b200 import geometry as G
+    cfg = tiny_config(n_views=9, channels=4)
+    scene = make_scene(cfg, 7)
+    meta = scene["img_meta"]
+    w2c = torch.tensor(np.array(meta["lidar2img"]["extrinsic"]))
+    c2w = w2c.inverse()
+    a = ref.get_nearest_pose_ids(c2w, c2w, 2, maskself=True)
+    b = G.get_nearest_pose_ids(c2w, c2w, 2, maskself=True)
+    assert torch.equal(a, b)
+    self = ref_loader.make_self(cfg.near_far_range, cfg.num_depth)
+    intr = torch.tensor(np.array(meta["lidar2img"]["intrinsic"]))
+    kf = G.feature_intrinsics(intr, cfg.ratio)
+    pa, na = ref.collect_proj(self, w2c, kf, a)
+    pb, nb = G.collect_proj(w2c, kf, b)
+    assert torch.equal(pa, pb) and all(torch.equal(x, y) for x, y in zip(na, nb))
+    assert torch.equal(ref._compute_projection(meta, cfg.stride, None),
+                       G.compute_projection(meta, cfg.stride))
+    pts = ref.get_points(n_voxels=torch.tensor(cfg.n_voxels), voxel_size=torch.tensor(cfg.voxel_size),
+                         origin=torch.tensor(meta["lidar2img"]["origin"]))
+    assert torch.equal(pts, G.get_points(cfg.n_voxels, cfg.voxel_size, meta["lidar2img"]["origin"]))
