@@ -114,6 +114,91 @@ __device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c) {
                      fmaf(a.w, b.w, c.w));
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2) -----------------------
+// ncu shows both sweep kernels bound by instruction issue (fwd: 81% issue-active),
+// not by a memory pipe; Blackwell's f32x2 arithmetic halves the math instruction
+// count.  Each lane's 4 channels live in two 64-bit register pairs.  Same fp32
+// rounding per element as the scalar ops (fma.rn / mul.rn / add.rn).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+struct P4 {               // 4 consecutive channels as two f32x2 pairs
+  u64 lo, hi;
+};
+__device__ __forceinline__ P4 p4zero() { return P4{0ull, 0ull}; }
+__device__ __forceinline__ P4 p4from(float4 v) { return P4{pk2(v.x, v.y), pk2(v.z, v.w)}; }
+__device__ __forceinline__ P4 p4from(uint2 r) {       // 4 x bf16
+  return P4{pk2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u)),
+            pk2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u))};
+}
+__device__ __forceinline__ float4 p4to(P4 a) {
+  float4 v;
+  upk2(a.lo, v.x, v.y);
+  upk2(a.hi, v.z, v.w);
+  return v;
+}
+__device__ __forceinline__ P4 p4scale(P4 a, u64 s) { return P4{mul2(a.lo, s), mul2(a.hi, s)}; }
+__device__ __forceinline__ P4 p4add(P4 a, P4 b) { return P4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
+__device__ __forceinline__ P4 p4sub(P4 a, P4 b) { return P4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
+__device__ __forceinline__ P4 p4mul(P4 a, P4 b) { return P4{mul2(a.lo, b.lo), mul2(a.hi, b.hi)}; }
+__device__ __forceinline__ P4 p4fma(P4 a, u64 s, P4 c) {
+  return P4{fma2(a.lo, s, c.lo), fma2(a.hi, s, c.hi)};
+}
+__device__ __forceinline__ P4 p4fma(P4 a, P4 b, P4 c) {
+  return P4{fma2(a.lo, b.lo, c.lo), fma2(a.hi, b.hi, c.hi)};
+}
+
+// raw (un-converted) 4-channel loads, so the bf16 -> fp32 shift/mask lands next
+// to the packed arithmetic that consumes it
+template <typename T> struct Raw;
+template <> struct Raw<float> {
+  typedef float4 type;
+  static __device__ __forceinline__ float4 ld(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+  }
+  static __device__ __forceinline__ float4 ld_stream(const float* p) {
+    return __ldcs(reinterpret_cast<const float4*>(p));
+  }
+  static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <> struct Raw<__nv_bfloat16> {
+  typedef uint2 type;
+  static __device__ __forceinline__ uint2 ld(const __nv_bfloat16* p) {
+    return __ldg(reinterpret_cast<const uint2*>(p));
+  }
+  static __device__ __forceinline__ uint2 ld_stream(const __nv_bfloat16* p) {
+    return __ldcs(reinterpret_cast<const uint2*>(p));
+  }
+  static __device__ __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
+};
+
 // 64-bit address = base + 32-bit unsigned element offset: one IMAD.WIDE.U32.
 template <typename T>
 __device__ __forceinline__ const T* at(const T* base, unsigned off) {
@@ -158,6 +243,37 @@ __device__ __forceinline__ void gather_taps(const TIn* __restrict__ src, const W
     w = f4fma(t01[g], s.w01, w);
     w = f4fma(t10[g], s.w10, w);
     wv[g] = f4fma(t11[g], s.w11, w);
+  }
+}
+
+// Packed variant of gather_taps: same tap order, FMUL2 / FFMA2.
+template <typename TIn, int G, bool FULL>
+__device__ __forceinline__ void gather_taps_p(const TIn* __restrict__ src, const WarpSample& s,
+                                              int c0, int C, P4 (&wv)[G]) {
+  const TIn* a00 = at(src, s.p00);
+  const TIn* a01 = at(src, s.p01);
+  const TIn* a10 = at(src, s.p10);
+  const TIn* a11 = at(src, s.p11);
+  typename Raw<TIn>::type t00[G], t01[G], t10[G], t11[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (group_on<FULL>(c0, g, C)) {
+      t00[g] = Raw<TIn>::ld(a00 + 128 * g);
+      t01[g] = Raw<TIn>::ld(a01 + 128 * g);
+      t10[g] = Raw<TIn>::ld(a10 + 128 * g);
+      t11[g] = Raw<TIn>::ld(a11 + 128 * g);
+    } else {
+      t00[g] = t01[g] = t10[g] = t11[g] = Raw<TIn>::zero();
+    }
+  }
+  const u64 w00 = pk2(s.w00, s.w00), w01 = pk2(s.w01, s.w01);
+  const u64 w10 = pk2(s.w10, s.w10), w11 = pk2(s.w11, s.w11);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    P4 w = p4scale(p4from(t00[g]), w00);
+    w = p4fma(p4from(t01[g]), w01, w);
+    w = p4fma(p4from(t10[g]), w10, w);
+    wv[g] = p4fma(p4from(t11[g]), w11, w);
   }
 }
 

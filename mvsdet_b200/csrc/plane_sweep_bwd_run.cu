@@ -209,6 +209,207 @@ __global__ void __launch_bounds__(kRunThreads, 4) sweep_bwd_run_kernel(const Swe
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Packed-arithmetic variant (default).  Same run-merging scheme; differences:
+//   * fp32 math on f32x2 pairs (FMUL2 / FFMA2 / FADD2): the scalar kernel issues
+//     ~390 instructions per pixel-plane and sits at 16 warps/SM;
+//   * the upstream-gradient stream (1.18 GB, the only DRAM-sized operand) is
+//     pulled into L2 two planes ahead with one cp.async.bulk.prefetch.L2 per
+//     warp and plane: ncu showed the scalar kernel waiting on exactly these
+//     loads (long-scoreboard 3.6 per issue at ~1 us DRAM latency with ~16 KB in
+//     flight per SM), now they are L2 hits and cost no registers;
+//   * neighbour base pointers are pinned in registers.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_p4(float* p, P4 v) {
+  float a, b, c, d;
+  upk2(v.lo, a, b);
+  upk2(v.hi, c, d);
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+
+template <int G, bool FULL>
+__device__ __forceinline__ void red_group_p(float* dst, unsigned off, const P4 (&v)[G], int c0,
+                                            int C) {
+  float* a = at(dst, off);
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+    if (group_on<FULL>(c0, g, C)) red_add_p4(a + 128 * g, v[g]);
+}
+
+template <int G, bool FULL>
+__device__ __forceinline__ void flush_open_p(float* dst, unsigned& id, const P4 (&acc)[G], int c0,
+                                             int C) {
+  if (id != kNoTap) red_group_p<G, FULL>(dst, id, acc, c0, C);
+  id = kNoTap;
+}
+
+template <int G, bool FULL>
+__device__ __forceinline__ void scatter_side_p(float* dst, const P4 (&gw)[G], float w_left,
+                                               float w_right, unsigned p_left, unsigned p_right,
+                                               unsigned& open_id, P4 (&open)[G], int c0, int C) {
+  const u64 wl = pk2(w_left, w_left), wr = pk2(w_right, w_right);
+  P4 a[G];
+  if (open_id == p_left) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = p4fma(gw[g], wl, open[g]);
+    red_group_p<G, FULL>(dst, p_left, a, c0, C);
+  } else {
+    flush_open_p<G, FULL>(dst, open_id, open, c0, C);
+    if (w_left != 0.f) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) a[g] = p4scale(gw[g], wl);
+      red_group_p<G, FULL>(dst, p_left, a, c0, C);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) open[g] = p4scale(gw[g], wr);
+  open_id = w_right != 0.f ? p_right : kNoTap;
+}
+
+constexpr int kPrefetchPlanes = 2;
+
+template <typename TIn, typename TG, int KMAX, int G, bool FULL>
+__global__ void __launch_bounds__(kRunThreads, 4) sweep_bwd_runp_kernel(const SweepParams p) {
+  __shared__ WarpSample s_tab[kRunRows][32];
+  __shared__ P4 s_gref[kRunRows][kRun][G][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RunCoord c = run_coord<G>(p, warp, lane);
+  if (c.y >= p.H) return;
+  const int C = p.C, k = p.k, HW = p.H * p.W;
+  const TIn* feat = static_cast<const TIn*>(p.feat);
+  const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+  const TIn* ref_row = feat + ref_off;
+  const size_t plane_stride = (size_t)HW * C;
+  const TG* g_d = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+  // L2 prefetch of this warp's slice of the run: npix pixels, (128*G or C-c0) channels each;
+  // with one channel slice (C <= 128*G) the run is one contiguous chunk.
+  const bool one_chunk = p.slices == 1;
+  const unsigned pf_bytes = (unsigned)((one_chunk ? (size_t)c.npix * C : (size_t)min(128 * G, C - (c.c0 - 4 * lane))) *
+                                       sizeof(TG)) & ~15u;
+  const TG* pf_base = g_d - 4 * lane;            // lane-independent start of the slice
+  const bool pf_ok = pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
+                     ((plane_stride * sizeof(TG)) & 15) == 0;
+  auto prefetch_plane = [&](int d) {
+    if (!pf_ok || d >= p.D) return;
+    const TG* q = pf_base + (size_t)d * plane_stride;
+    if (one_chunk) {
+      if (lane == 0) prefetch_l2(q, pf_bytes);
+    } else if (lane < c.npix) {
+      prefetch_l2(q + (size_t)lane * C, pf_bytes);
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kPrefetchPlanes; ++d) prefetch_plane(d);
+
+  const TIn* nsrc[KMAX];
+  float* ndst[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    int n = c.v + p.ref_begin;
+    if (j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
+    nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+    ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+    asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+  }
+  const float inv_n = 1.0f / (float)(k + 1);
+  const u64 inv_n2 = pk2(inv_n, inv_n);
+  const u64 two_inv_n2 = pk2(2.0f * inv_n, 2.0f * inv_n);
+  const int spp = kRun * k;
+  const int ppf = max(1, 32 / spp);
+
+#pragma unroll
+  for (int i = 0; i < kRun; ++i)
+#pragma unroll
+    for (int g = 0; g < G; ++g) s_gref[warp][i][g][lane] = p4zero();
+
+  for (int d0 = 0; d0 < p.D; d0 += ppf) {
+    __syncwarp();
+    fill_run_samples(s_tab[warp], p, c, d0, ppf, lane);
+    __syncwarp();
+    const int dend = min(p.D, d0 + ppf);
+    for (int d = d0; d < dend; ++d) {
+      prefetch_plane(d + kPrefetchPlanes);
+      P4 open_top[KMAX][G], open_bot[KMAX][G];
+      unsigned o_top[KMAX], o_bot[KMAX];
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        o_top[j] = o_bot[j] = kNoTap;
+#pragma unroll
+        for (int g = 0; g < G; ++g) open_top[j][g] = open_bot[j][g] = p4zero();
+      }
+      const WarpSample* tab = s_tab[warp] + (d - d0) * spp;
+#pragma unroll 1
+      for (int i = 0; i < c.npix; ++i) {
+        P4 gv[G], ref[G], mu[G];
+        P4 wv[KMAX][G];
+        WarpSample smp[KMAX];
+        typename Raw<TG>::type graw[G];
+        typename Raw<TIn>::type rraw[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const bool on = group_on<FULL>(c.c0, g, C);
+          graw[g] = on ? Raw<TG>::ld_stream(g_d + i * C + 128 * g) : Raw<TG>::zero();
+          rraw[g] = on ? Raw<TIn>::ld(ref_row + i * C + 128 * g) : Raw<TIn>::zero();
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) wv[j][g] = p4zero();
+          if (j >= k) continue;
+          smp[j] = tab[i * k + j];
+          if (smp[j].p00 == kNoSample) continue;
+          gather_taps_p<TIn, G, FULL>(nsrc[j], smp[j], c.c0, C, wv[j]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          ref[g] = p4from(rraw[g]);
+          mu[g] = ref[g];
+#pragma unroll
+          for (int j = 0; j < KMAX; ++j)
+            if (j < k) mu[g] = p4add(mu[g], wv[j][g]);
+          mu[g] = p4scale(mu[g], inv_n2);
+          gv[g] = p4scale(p4from(graw[g]), two_inv_n2);
+          s_gref[warp][i][g][lane] = p4fma(gv[g], p4sub(ref[g], mu[g]), s_gref[warp][i][g][lane]);
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          if (j >= k) continue;
+          const WarpSample s = smp[j];
+          if (s.p00 == kNoSample) {
+            flush_open_p<G, FULL>(ndst[j], o_top[j], open_top[j], c.c0, C);
+            flush_open_p<G, FULL>(ndst[j], o_bot[j], open_bot[j], c.c0, C);
+            continue;
+          }
+          P4 gw[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) gw[g] = p4mul(gv[g], p4sub(wv[j][g], mu[g]));
+          scatter_side_p<G, FULL>(ndst[j], gw, s.w00, s.w01, s.p00, s.p01, o_top[j], open_top[j], c.c0, C);
+          scatter_side_p<G, FULL>(ndst[j], gw, s.w10, s.w11, s.p10, s.p11, o_bot[j], open_bot[j], c.c0, C);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j >= k) continue;
+        flush_open_p<G, FULL>(ndst[j], o_top[j], open_top[j], c.c0, C);
+        flush_open_p<G, FULL>(ndst[j], o_bot[j], open_bot[j], c.c0, C);
+      }
+      g_d += plane_stride;
+    }
+  }
+  float* dst = p.g_feat + ref_off;
+  for (int i = 0; i < c.npix; ++i) {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, s_gref[warp][i][g][lane]);
+  }
+}
+
 // k in {1,2} only (k*kRun <= 32 samples per plane); other k use the pixel kernel.
 template <typename TIn, typename TG>
 static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
@@ -220,8 +421,12 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   if (blocks > 2147483647LL) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_bwd: grid too large");
   dim3 grid((unsigned)blocks);
   const bool full = p.C % (128 * G) == 0;
-#define MVSD_RUN(KM, GG, FU) \
-  sweep_bwd_run_kernel<TIn, TG, KM, GG, FU><<<grid, kRunThreads, 0, st>>>(p)
+  const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel
+#define MVSD_RUN(KM, GG, FU)                                                              \
+  do {                                                                                    \
+    if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU><<<grid, kRunThreads, 0, st>>>(p); \
+    else sweep_bwd_run_kernel<TIn, TG, KM, GG, FU><<<grid, kRunThreads, 0, st>>>(p);        \
+  } while (0)
   if (p.k == 1) {
     if (G == 2) { if (full) MVSD_RUN(1, 2, true); else MVSD_RUN(1, 2, false); }
     else { if (full) MVSD_RUN(1, 1, true); else MVSD_RUN(1, 1, false); }

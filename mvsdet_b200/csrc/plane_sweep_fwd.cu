@@ -85,6 +85,133 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
   }
 }
 
+// Packed-arithmetic forward (default): identical decomposition, the per-lane 4-channel
+// vectors are f32x2 pairs so the bilinear blend and the S1 / S2 accumulation
+// issue as FMUL2 / FFMA2 / FADD2 -- the scalar kernel above is issue-bound
+// (profiles/r01_a_ncu_sweep_summary.txt: 81% issue-active, 314 instructions per
+// pixel-plane of which 160 are fp32 math).
+template <typename TIn, typename TOut, int KMAX, int G, bool FULL>
+__global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepParams p) {
+  __shared__ WarpSample s_tab[kSweepWarps][kSlots];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const SweepCoord c = sweep_coord<G>(p, warp, lane);
+  if (!c.ok) return;
+  const int C = p.C, k = p.k, HW = p.H * p.W;
+  const TIn* feat = static_cast<const TIn*>(p.feat);
+  const unsigned pix = (unsigned)(c.y * p.W + c.x);
+  TOut* out_pix = static_cast<TOut*>(p.out) + ((size_t)c.v * p.D * HW + pix) * C + c.c0;
+  const size_t plane_stride = (size_t)HW * C;
+
+  P4 ref[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    ref[g] = p4zero();
+    if (group_on<FULL>(c.c0, g, C))
+      ref[g] = p4from(Raw<TIn>::ld(feat + ((size_t)(c.v + p.ref_begin) * HW + pix) * C + c.c0 + 128 * g));
+  }
+  TOut* o = out_pix;
+  const TIn* nsrc[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    int n = c.v + p.ref_begin;
+    if (j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
+    nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+    asm volatile("" : "+l"(nsrc[j]));           // keep the base in registers (ptxas re-derives it per plane otherwise)
+  }
+  const float inv_n = 1.0f / (float)(k + 1);
+  const u64 inv_n2 = pk2(inv_n, inv_n);
+  const int dc = k > 0 ? kSlots / k : p.D;
+
+  for (int d0 = 0; d0 < p.D; d0 += dc) {
+    if (k > 0) {
+      __syncwarp();
+      fill_samples(s_tab[warp], p, c, d0, dc, lane);
+      __syncwarp();
+    }
+    const int dend = min(p.D, d0 + dc);
+    for (int d = d0; d < dend; ++d) {
+      const WarpSample* tab = s_tab[warp] + (d - d0) * k;
+      // The variance + store tail is instantiated once per control path (which
+      // neighbours have a sample), so no path pays register moves at a merge.
+      auto emit = [&](const P4 (&s1)[G], const P4 (&s2)[G]) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (!group_on<FULL>(c.c0, g, C)) continue;
+          // var = S2/n - (S1/n)^2, every step rounded on its own (see the scalar kernel)
+          const float4 m = p4to(p4scale(s1[g], inv_n2));
+          const float4 q = p4to(p4scale(s2[g], inv_n2));
+          float4 r;
+          r.x = __fsub_rn(q.x, __fmul_rn(m.x, m.x));
+          r.y = __fsub_rn(q.y, __fmul_rn(m.y, m.y));
+          r.z = __fsub_rn(q.z, __fmul_rn(m.z, m.z));
+          r.w = __fsub_rn(q.w, __fmul_rn(m.w, m.w));
+          Io<TOut>::st_stream(o + 128 * g, r);
+        }
+      };
+      if (KMAX <= 2) {
+        const bool v0 = k > 0 && tab[0].p00 != kNoSample;
+        const bool v1 = KMAX == 2 && k > 1 && tab[1].p00 != kNoSample;
+        if (v0) {
+          P4 s1[G], s2[G], wv[G];
+          gather_taps_p<TIn, G, FULL>(nsrc[0], tab[0], c.c0, C, wv);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            s1[g] = p4add(ref[g], wv[g]);
+            s2[g] = p4fma(wv[g], wv[g], p4mul(ref[g], ref[g]));
+          }
+          if (v1) {
+            gather_taps_p<TIn, G, FULL>(nsrc[KMAX - 1], tab[KMAX - 1], c.c0, C, wv);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              s1[g] = p4add(s1[g], wv[g]);
+              s2[g] = p4fma(wv[g], wv[g], s2[g]);
+            }
+            emit(s1, s2);
+          } else {
+            emit(s1, s2);
+          }
+        } else if (v1) {
+          P4 s1[G], s2[G], wv[G];
+          gather_taps_p<TIn, G, FULL>(nsrc[KMAX - 1], tab[KMAX - 1], c.c0, C, wv);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            s1[g] = p4add(ref[g], wv[g]);
+            s2[g] = p4fma(wv[g], wv[g], p4mul(ref[g], ref[g]));
+          }
+          emit(s1, s2);
+        } else {
+          P4 s2[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) s2[g] = p4mul(ref[g], ref[g]);
+          emit(ref, s2);
+        }
+      } else {
+        P4 s1[G], s2[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          s1[g] = ref[g];
+          s2[g] = p4mul(ref[g], ref[g]);
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          if (j >= k) break;
+          if (tab[j].p00 == kNoSample) continue;   // all four taps outside: adds 0
+          P4 wv[G];
+          gather_taps_p<TIn, G, FULL>(nsrc[j], tab[j], c.c0, C, wv);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            s1[g] = p4add(s1[g], wv[g]);
+            s2[g] = p4fma(wv[g], wv[g], s2[g]);
+          }
+        }
+        emit(s1, s2);
+      }
+      o += plane_stride;
+      asm volatile("" : "+l"(o));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -126,8 +253,12 @@ static int launch_fwd_k(SweepParams& p, cudaStream_t st) {
   if (!sweep_grid(p, G, grid)) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_fwd: grid too large");
   const bool full = p.C % (128 * G) == 0;
   const int kmax = WARP_ONLY ? 1 : (p.k <= 1 ? 1 : (p.k == 2 ? 2 : 4));
-#define MVSD_FWD(KM, GG, FU) \
-  sweep_fwd_kernel<TIn, TOut, KM, GG, FU, WARP_ONLY><<<grid, kSweepThreads, 0, st>>>(p)
+  const bool packed = !WARP_ONLY && tuning(6) != 1;   // tuning key 6: 1 = scalar-math kernel
+#define MVSD_FWD(KM, GG, FU)                                                           \
+  do {                                                                                 \
+    if (packed) sweep_fwd_p_kernel<TIn, TOut, KM, GG, FU><<<grid, kSweepThreads, 0, st>>>(p); \
+    else sweep_fwd_kernel<TIn, TOut, KM, GG, FU, WARP_ONLY><<<grid, kSweepThreads, 0, st>>>(p); \
+  } while (0)
 #define MVSD_FWD_G(KM)                                                            \
   do {                                                                            \
     if (G == 2) { if (full) MVSD_FWD(KM, 2, true); else MVSD_FWD(KM, 2, false); } \

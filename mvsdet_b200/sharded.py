@@ -1,0 +1,134 @@
+"""View-sharded forward of ONE scene over the ranks of a process group
+(BASELINE.json configs[2]: test-time scenes with 50-100 source views).
+
+Reference views are independent in the plane sweep and in the back-projection
+(per-view loops, projects/NeRF-Det/nerfdet/mvsdet.py:453, :1401, :1458); only
+the sum over views and the per-voxel valid count couple them (mvsdet.py:511-515).
+So every rank sweeps a contiguous block of reference views, back-projects them
+into *partial* voxel sums and counts (``MVSD_BP_SUM``), the partials are
+combined with ONE all-reduce of ``C*N + N`` fp32 words (26.3 MB for the shipped
+40x40x16 grid) -- NCCL over NVLink on the B200 box -- and every rank applies the
+same ``sum / (count + 1e-8)`` (mvsdet.py:514-515, :681-682), giving replicas
+that are bit-identical across ranks.  The counts travel as fp32 in the same
+buffer: they are integers <= V <= 2^24, so the sum is exact.
+
+The FPN feature maps of all V views are resident on every rank (the k=2 pose
+neighbours of a local view may belong to another rank, SURVEY.md 8e caveat 1);
+only the reference-view work is partitioned.
+
+The partition / packing / all-reduce helpers are device-agnostic host logic and
+are exercised with a world-size-2 gloo group on CPU (tests/test_sharded_cpu.py);
+``ShardedSceneForward`` itself launches the CUDA kernels and needs a GPU.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["partition_views", "pack_partials", "unpack_partials", "allreduce_partials",
+           "ShardedSceneForward"]
+
+
+def partition_views(n_views: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced block [begin, end) of reference views for ``rank``
+    (the first ``n_views % world_size`` ranks get one extra view; a rank may get
+    an empty block when world_size > n_views)."""
+    if n_views < 0 or world_size <= 0 or not 0 <= rank < world_size:
+        raise ValueError(f"bad partition request: V={n_views}, world={world_size}, rank={rank}")
+    base, extra = divmod(n_views, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def pack_partials(volume_sum: torch.Tensor, count: torch.Tensor,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[C,N] fp32 sums (any memory order) + [N] integer counts -> one flat fp32
+    buffer ``[C*N + N]`` in the memory order of ``volume_sum``."""
+    c, n = volume_sum.shape
+    if count.numel() != n:
+        raise ValueError("count must have one entry per voxel")
+    mem = volume_sum if volume_sum.is_contiguous() else volume_sum.t()
+    if not mem.is_contiguous():
+        raise ValueError("volume_sum must be [C,N] contiguous or the transpose of a contiguous [N,C]")
+    if out is None:
+        out = torch.empty(c * n + n, dtype=torch.float32, device=volume_sum.device)
+    out[:c * n].copy_(mem.reshape(-1))
+    out[c * n:].copy_(count.reshape(-1))       # int -> fp32, exact for counts <= 2^24
+    return out
+
+
+def unpack_partials(buf: torch.Tensor, c: int, n: int, channels_first: bool = True):
+    """Inverse of pack_partials -> (volume_sum logical [C,N] view, count int32 [N])."""
+    vol = buf[:c * n].view(c, n) if channels_first else buf[:c * n].view(n, c).t()
+    count = buf[c * n:].round().to(torch.int32)
+    return vol, count
+
+
+def allreduce_partials(buf: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the packed partials over the group, in place.  One collective per
+    scene; a no-op without an initialised process group (single-rank run)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
+
+
+class ShardedSceneForward:
+    """Forward of one scene with the reference views split over the group.
+
+        sharded = ShardedSceneForward(hot_path)            # an MVSDetHotPath
+        out = sharded(feature, img_meta, cost_regularization)
+        out["volume_mean"], out["count"]                   # identical on every rank
+
+    ``feature`` holds ALL views on every rank.  The all-reduce runs on the
+    current stream right after the local back-projection (there is nothing left
+    to overlap it with inside one scene; a multi-scene caller overlaps it with
+    the next scene's sweep by calling from a side stream)."""
+
+    def __init__(self, hot_path, group=None):
+        self.hot = hot_path
+        self.group = group
+
+    def _world(self) -> Tuple[int, int]:
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(self.group), dist.get_world_size(self.group)
+        return 0, 1
+
+    def __call__(self, feature: torch.Tensor, img_meta: dict,
+                 cost_regularization: Optional[Callable] = None) -> Dict[str, torch.Tensor]:
+        from . import ops
+        hot = self.hot
+        cost_net = cost_regularization or hot.cost_regularization
+        if cost_net is None:
+            raise ValueError("a cost_regularization callable is required (mvsdet.py:470)")
+        rank, world = self._world()
+        v_all = feature.shape[0]
+        begin, end = partition_views(v_all, world, rank)
+        feat_cl = ops.pack_features(feature, hot.feature_dtype)
+        c = feat_cl.shape[1]
+        nx, ny, nz = hot.n_voxels
+        n = nx * ny * nz
+        dev = feature.device
+        if end > begin:
+            geo = hot.geometry(img_meta, dev, view_slice=slice(begin, end))
+            variance = hot.variance(feat_cl, geo, ref_begin=begin)
+            cost_out = cost_net(variance)
+            _, _, est_depth, est_dens, est_idx, _ = hot.hypotheses(cost_out)
+            vol_sum, count = ops.backproject_aggregate(
+                feat_cl[begin:end], geo.points, geo.projection, est_depth, est_dens,
+                hot.voxel_size[2], geo.height, geo.width, mode="sum",
+                channels_first=hot.channels_first_volume)
+        else:                                   # more ranks than views: contribute zeros
+            shape = (c, n) if hot.channels_first_volume else (n, c)
+            vol_sum = torch.zeros(shape, dtype=torch.float32, device=dev)
+            vol_sum = vol_sum if hot.channels_first_volume else vol_sum.t()
+            count = torch.zeros(n, dtype=torch.int32, device=dev)
+        buf = pack_partials(vol_sum.detach(), count)
+        allreduce_partials(buf, self.group)
+        vol_sum, count = unpack_partials(buf, c, n, hot.channels_first_volume)
+        volume_mean = ops.voxel_normalize(vol_sum, count)
+        vm = (volume_mean.view(c, nx, ny, nz) if volume_mean.is_contiguous()
+              else volume_mean.unflatten(1, (nx, ny, nz)))
+        return dict(volume_mean=vm, valid=count.view(1, nx, ny, nz).float(), count=count,
+                    view_range=(begin, end))
