@@ -223,3 +223,75 @@ class ScenePipeline:
             self.step()
         for n in self.OUTPUTS:
             host[n].copy_(getattr(self, n), non_blocking=True)
+
+
+class HostPipelinedRunner:
+    """Host-buffer steps over several ``ScenePipeline`` buffer sets with the
+    copies overlapped with compute: three streams (H2D, compute, D2H), step i
+    uses buffer set i % n.  Every step still copies its own inputs in from
+    pinned host memory and its own results out; only the *overlap* differs from
+    ``ScenePipeline.run_host``.  PCIe is full duplex, so the steady state is
+    bound by the slowest of {H2D, compute, D2H}.
+
+        runner = HostPipelinedRunner(pipes, graphs)
+        runner.run(host_inputs, n_steps)      # enqueue; returns (start, end) events
+    """
+
+    def __init__(self, pipes, graphs=None):
+        if not pipes:
+            raise ValueError("need at least one ScenePipeline")
+        self.pipes = list(pipes)
+        self.graphs = list(graphs) if graphs else [None] * len(self.pipes)
+        dev = self.pipes[0].device
+        self.s_in = torch.cuda.Stream(device=dev)
+        self.s_run = torch.cuda.Stream(device=dev)
+        self.s_out = torch.cuda.Stream(device=dev)
+        self._ev_run = [None] * len(self.pipes)     # last compute on the set (inputs consumed)
+        self._ev_out = [None] * len(self.pipes)     # last D2H of the set (outputs drained)
+
+    def run(self, host_inputs: Dict[str, torch.Tensor], n_steps: int):
+        """Enqueue ``n_steps`` host-buffer steps.  ``host_inputs`` are pinned
+        tensors named as ScenePipeline.INPUTS; results land in each set's
+        ``host_buffers()``.  Returns (start_event, end_event) recorded around the
+        whole region; the caller synchronises."""
+        cur = torch.cuda.current_stream()
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(cur)
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record(self.s_in)
+        n = len(self.pipes)
+        for i in range(n_steps):
+            b = i % n
+            p = self.pipes[b]
+            host_out = p.host_buffers()
+            with torch.cuda.stream(self.s_in):
+                if self._ev_run[b] is not None:
+                    self.s_in.wait_event(self._ev_run[b])
+                for name in p.INPUTS:
+                    getattr(p, name).copy_(host_inputs[name], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(ev_in)
+                if self._ev_out[b] is not None:
+                    self.s_run.wait_event(self._ev_out[b])
+                if self.graphs[b] is not None:
+                    self.graphs[b].replay()
+                else:
+                    p.step()
+                ev_run = torch.cuda.Event()
+                ev_run.record(self.s_run)
+                self._ev_run[b] = ev_run
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_run)
+                for name in p.OUTPUTS:
+                    host_out[name].copy_(getattr(p, name), non_blocking=True)
+                ev_out = torch.cuda.Event()
+                ev_out.record(self.s_out)
+                self._ev_out[b] = ev_out
+        self.s_out.wait_stream(self.s_in)
+        self.s_out.wait_stream(self.s_run)
+        end.record(self.s_out)
+        cur.wait_stream(self.s_out)
+        return start, end

@@ -1,0 +1,104 @@
+"""Host logic of the view-sharded scene forward (mvsdet_b200/sharded.py) on CPU:
+partitioning, packing and a REAL world-size-2 all-reduce over gloo.  The
+per-rank partial voxel sums come from the oracle (test infrastructure) -- on a
+GPU box the same partials come from mvsd_backproject_fwd(MVSD_BP_SUM), which
+tests/test_gpu_parity.py::test_view_sharded_partials_match_whole_scene covers.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import load_golden, oracle_chain
+from mvsdet_b200 import sharded
+from oracle import mvsdet_oracle as O
+
+
+def test_partition_views_covers_everything_once():
+    for v in (0, 1, 2, 5, 20, 80, 81, 100):
+        for world in (1, 2, 3, 4, 8, 16):
+            blocks = [sharded.partition_views(v, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == v
+            for (b0, e0), (b1, e1) in zip(blocks, blocks[1:]):
+                assert e0 == b1 and e0 >= b0 and e1 >= b1
+            sizes = [e - b for b, e in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharded.partition_views(4, 2, 2)
+
+
+def test_pack_unpack_roundtrip_both_memory_orders():
+    g = torch.Generator().manual_seed(3)
+    c, n = 8, 50
+    vol = torch.randn(c, n, generator=g)
+    cnt = torch.randint(0, 100, (n,), generator=g, dtype=torch.int32)
+    buf = sharded.pack_partials(vol, cnt)
+    assert buf.shape == (c * n + n,) and buf.dtype == torch.float32
+    v2, c2 = sharded.unpack_partials(buf, c, n, channels_first=True)
+    assert torch.equal(v2, vol) and torch.equal(c2, cnt)
+    vol_t = torch.randn(n, c, generator=g).t()              # logical [C,N], memory [N,C]
+    buf = sharded.pack_partials(vol_t, cnt)
+    v3, c3 = sharded.unpack_partials(buf, c, n, channels_first=False)
+    assert torch.equal(v3, vol_t) and torch.equal(c3, cnt)
+    with pytest.raises(ValueError):
+        sharded.pack_partials(vol, cnt[:-1])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _partials_for(scene, full, begin, end):
+    """Partial voxel sums / counts of reference views [begin, end) with the
+    oracle's back-projection fed the whole-scene hypotheses."""
+    cfg = scene["cfg"]
+    h, w = cfg.crop_hw
+    v = end - begin
+    depth = full["est_depth"][begin:end, :, :h, :w].reshape(v, cfg.topk, -1).transpose(2, 1).unsqueeze(2)
+    dens = full["est_densities"][begin:end, :, :h, :w].reshape(v, cfg.topk, -1).transpose(2, 1).unsqueeze(2)
+    vol, valid = O.backproject_weigh(scene["feature"][begin:end, :, :h, :w], full["points"],
+                                     full["projection"][begin:end], depth, cfg.voxel_size, dens)
+    c = vol.shape[1]
+    return vol.sum(0).reshape(c, -1), valid.sum(0).reshape(-1).to(torch.int32)
+
+
+def _worker(rank, world, port, case, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        scene, _ = load_golden(case)
+        full = oracle_chain(scene, with_grads=False)
+        begin, end = sharded.partition_views(scene["cfg"].n_views, world, rank)
+        vol_sum, count = _partials_for(scene, full, begin, end)
+        c, n = vol_sum.shape
+        buf = sharded.pack_partials(vol_sum, count)
+        sharded.allreduce_partials(buf)                                 # the one collective
+        tot, cnt = sharded.unpack_partials(buf, c, n)
+        mean = torch.where(cnt.unsqueeze(0) == 0, torch.zeros_like(tot), tot / (cnt + 1e-8))
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), mean=mean.numpy(), count=cnt.numpy(),
+                 want_mean=full["volume_mean"].reshape(c, n).numpy(),
+                 want_count=full["count"].reshape(-1).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["scannet_tiny", "arkit_tiny"])
+def test_two_rank_gloo_allreduce_reproduces_whole_scene(case, tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for r in res:
+        assert np.array_equal(r["count"], r["want_count"]), "voxel counts must be bit-exact"
+        np.testing.assert_allclose(r["mean"], r["want_mean"], rtol=1e-5, atol=1e-6)
+    # replicas are bit-identical after the all-reduce + identical normalisation
+    assert np.array_equal(res[0]["mean"], res[1]["mean"])
+    assert np.array_equal(res[0]["count"], res[1]["count"])
