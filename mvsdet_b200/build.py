@@ -22,7 +22,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvsdet_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
-SOURCES = ("capi.cu", "pack.cu", "plane_sweep_fwd.cu", "plane_sweep_bwd.cu", "plane_sweep_bwd_run.cu",
+SOURCES = ("capi.cu", "pack.cu", "plane_sweep_fwd.cu", "plane_sweep_bwd.cu", "plane_sweep_bwd_run.cu", "plane_sweep_bwd_blk.cu",
            "depth_topk.cu",
            "backproject.cu")
 HEADERS = (os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "plane_sweep.cuh"),

@@ -136,6 +136,7 @@ static int launch_bwd_k(SweepParams& p, cudaStream_t st) {
 }
 
 int launch_bwd_run(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st);
+int launch_bwd_blk(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st);
 
 }  // namespace mvsd
 
@@ -154,8 +155,12 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   p.g_feat = g_feat;
   p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // tuning key 5: 0/unset = run-merging variant when applicable, 1 = pixel kernel
-  if ((k == 1 || k == 2) && tuning(5) != 1) return launch_bwd_run(p, feat_dtype, g_dtype, st);
+  // tuning key 5: 0/unset = packed run-merging kernel (k <= 2), 1 = pixel kernel,
+  // 2 = scalar run-merging kernel, 4 = block-merging kernel (TMEM + row cache; fewer
+  // REDs but more instructions: measured slower)
+  const int variant = tuning(5);
+  if ((k == 1 || k == 2) && variant == 4) return launch_bwd_blk(p, feat_dtype, g_dtype, st);
+  if ((k == 1 || k == 2) && variant != 1) return launch_bwd_run(p, feat_dtype, g_dtype, st);
   if (feat_dtype == MVSD_F32 && g_dtype == MVSD_F32) return launch_bwd_k<float, float, false>(p, st);
   if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_F32)
     return launch_bwd_k<__nv_bfloat16, float, false>(p, st);

@@ -274,8 +274,8 @@ __device__ __forceinline__ void scatter_side_p(float* dst, const P4 (&gw)[G], fl
 
 constexpr int kPrefetchPlanes = 2;
 
-template <typename TIn, typename TG, int KMAX, int G, bool FULL>
-__global__ void __launch_bounds__(kRunThreads, 4) sweep_bwd_runp_kernel(const SweepParams p) {
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB>
+__global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runp_kernel(const SweepParams p) {
   __shared__ WarpSample s_tab[kRunRows][32];
   __shared__ P4 s_gref[kRunRows][kRun][G][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -357,14 +357,21 @@ __global__ void __launch_bounds__(kRunThreads, 4) sweep_bwd_runp_kernel(const Sw
           graw[g] = on ? Raw<TG>::ld_stream(g_d + i * C + 128 * g) : Raw<TG>::zero();
           rraw[g] = on ? Raw<TIn>::ld(ref_row + i * C + 128 * g) : Raw<TIn>::zero();
         }
+        // all loads of the pixel (gradient, reference, both neighbours' taps) go out
+        // before the first dependent instruction: one L2 round trip per pixel, not three
+        RawTaps<TIn, G> traw[KMAX];
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          if (j >= k) continue;
+          smp[j] = tab[i * k + j];
+          if (smp[j].p00 != kNoSample) load_taps<TIn, G, FULL>(nsrc[j], smp[j], c.c0, C, traw[j]);
+        }
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
 #pragma unroll
           for (int g = 0; g < G; ++g) wv[j][g] = p4zero();
-          if (j >= k) continue;
-          smp[j] = tab[i * k + j];
-          if (smp[j].p00 == kNoSample) continue;
-          gather_taps_p<TIn, G, FULL>(nsrc[j], smp[j], c.c0, C, wv[j]);
+          if (j >= k || smp[j].p00 == kNoSample) continue;
+          blend_taps<TIn, G>(traw[j], smp[j], wv[j]);
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -421,10 +428,12 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   if (blocks > 2147483647LL) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_bwd: grid too large");
   dim3 grid((unsigned)blocks);
   const bool full = p.C % (128 * G) == 0;
-  const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel
+  const bool minb3 = tuning(4) != 1;       // tuning key 4: 1 = cap at 128 registers (4 CTAs/SM) instead of 168 (3)
+  const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel, 3 = packed
 #define MVSD_RUN(KM, GG, FU)                                                              \
   do {                                                                                    \
-    if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU><<<grid, kRunThreads, 0, st>>>(p); \
+    if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4><<<grid, kRunThreads, 0, st>>>(p); \
     else sweep_bwd_run_kernel<TIn, TG, KM, GG, FU><<<grid, kRunThreads, 0, st>>>(p);        \
   } while (0)
   if (p.k == 1) {

@@ -151,7 +151,21 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepP
       if (KMAX <= 2) {
         const bool v0 = k > 0 && tab[0].p00 != kNoSample;
         const bool v1 = KMAX == 2 && k > 1 && tab[1].p00 != kNoSample;
-        if (v0) {
+        if (v0 && v1) {
+          // both neighbours' 8*G loads in flight before the first blend
+          RawTaps<TIn, G> r0, r1;
+          load_taps<TIn, G, FULL>(nsrc[0], tab[0], c.c0, C, r0);
+          load_taps<TIn, G, FULL>(nsrc[KMAX - 1], tab[KMAX - 1], c.c0, C, r1);
+          P4 s1[G], s2[G], wa[G], wb[G];
+          blend_taps<TIn, G>(r0, tab[0], wa);
+          blend_taps<TIn, G>(r1, tab[KMAX - 1], wb);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            s1[g] = p4add(p4add(ref[g], wa[g]), wb[g]);
+            s2[g] = p4fma(wb[g], wb[g], p4fma(wa[g], wa[g], p4mul(ref[g], ref[g])));
+          }
+          emit(s1, s2);
+        } else if (v0) {
           P4 s1[G], s2[G], wv[G];
           gather_taps_p<TIn, G, FULL>(nsrc[0], tab[0], c.c0, C, wv);
 #pragma unroll
@@ -159,17 +173,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepP
             s1[g] = p4add(ref[g], wv[g]);
             s2[g] = p4fma(wv[g], wv[g], p4mul(ref[g], ref[g]));
           }
-          if (v1) {
-            gather_taps_p<TIn, G, FULL>(nsrc[KMAX - 1], tab[KMAX - 1], c.c0, C, wv);
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              s1[g] = p4add(s1[g], wv[g]);
-              s2[g] = p4fma(wv[g], wv[g], s2[g]);
-            }
-            emit(s1, s2);
-          } else {
-            emit(s1, s2);
-          }
+          emit(s1, s2);
         } else if (v1) {
           P4 s1[G], s2[G], wv[G];
           gather_taps_p<TIn, G, FULL>(nsrc[KMAX - 1], tab[KMAX - 1], c.c0, C, wv);

@@ -95,8 +95,17 @@ class ShardedSceneForward:
             return dist.get_rank(self.group), dist.get_world_size(self.group)
         return 0, 1
 
+    def local_geometry(self, img_meta: dict, n_views: int, device):
+        """This rank's slice of the per-scene parameter block (host work, ~2 ms;
+        a caller that revisits a scene passes it back in as ``geometry``)."""
+        rank, world = self._world()
+        begin, end = partition_views(n_views, world, rank)
+        if end <= begin:
+            return None
+        return self.hot.geometry(img_meta, device, view_slice=slice(begin, end))
+
     def __call__(self, feature: torch.Tensor, img_meta: dict,
-                 cost_regularization: Optional[Callable] = None) -> Dict[str, torch.Tensor]:
+                 cost_regularization: Optional[Callable] = None, geometry=None) -> Dict[str, torch.Tensor]:
         from . import ops
         hot = self.hot
         cost_net = cost_regularization or hot.cost_regularization
@@ -111,7 +120,7 @@ class ShardedSceneForward:
         n = nx * ny * nz
         dev = feature.device
         if end > begin:
-            geo = hot.geometry(img_meta, dev, view_slice=slice(begin, end))
+            geo = geometry or hot.geometry(img_meta, dev, view_slice=slice(begin, end))
             variance = hot.variance(feat_cl, geo, ref_begin=begin)
             cost_out = cost_net(variance)
             _, _, est_depth, est_dens, est_idx, _ = hot.hypotheses(cost_out)

@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""View-sharded forward of one test-time scene (BASELINE.json configs[2]) over
+the ranks of a torchrun job: checks the sharded result against the whole-scene
+result of one GPU and times both (CUDA events, max over ranks).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/run_sharded.py --views 80
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from mvsdet_b200 import sharded  # noqa: E402
+from mvsdet_b200.hotpath import MVSDetHotPath  # noqa: E402
+from mvsdet_b200.scene import SceneConfig, make_scene  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--views", type=int, default=80)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--feature-dtype", default="bf16")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = SceneConfig(n_views=a.views)
+    scene = make_scene(cfg, seed=7, with_grads=False)          # same scene on every rank
+    fdt = torch.bfloat16 if a.feature_dtype == "bf16" else torch.float32
+    hot = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
+                        feature_dtype=fdt)
+    feat = scene["feature"].to(dev)
+    cost = scene["cost_out"].to(dev)
+    begin, end = sharded.partition_views(cfg.n_views, world, rank)
+    runner = sharded.ShardedSceneForward(hot)
+    geo_local = runner.local_geometry(scene["img_meta"], cfg.n_views, dev)
+    geo_full = hot.geometry(scene["img_meta"], dev)
+
+    def sharded_fwd():
+        return runner(feat, scene["img_meta"], cost_regularization=lambda var: cost[begin:end],
+                      geometry=geo_local)
+
+    def whole_fwd():
+        return hot(feat, scene["img_meta"], cost_regularization=lambda var: cost, geometry=geo_full)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.iters
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    ms_sh, out_sh = timed(sharded_fwd)
+    res = {"views": cfg.n_views, "world": world, "ms_sharded_forward": round(ms_sh, 4),
+           "scenes_per_s_sharded": round(1e3 / ms_sh, 2), "feature_dtype": a.feature_dtype,
+           "allreduce_bytes": int(out_sh["volume_mean"].numel() * 4 + out_sh["count"].numel() * 4),
+           "neighbour_features": "replicated on every rank"}
+    if rank == 0:
+        ms_w, out_w = timed(whole_fwd) if world == 1 else (None, None)
+    if world > 1:
+        # every rank computes the whole scene once for the check (rank 0 also times it afterwards)
+        out_w = whole_fwd()
+        same_count = bool(torch.equal(out_sh["count"], out_w["count"]))
+        err = float((out_sh["volume_mean"] - out_w["volume_mean"]).abs().max())
+        ref = float(out_w["volume_mean"].abs().max())
+        flags = torch.tensor([int(same_count), int(err <= 1e-5 * max(ref, 1.0))], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        # replicas bit-identical across ranks?
+        chk = out_sh["volume_mean"].double().sum().reshape(1)
+        gathered = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        res.update(counts_bit_exact=bool(flags[0].item()), volume_close=bool(flags[1].item()),
+                   max_abs_err=err, replicas_identical=all(float(g) == float(gathered[0]) for g in gathered))
+        dist.barrier()
+        if rank == 0:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                whole_fwd()
+            e0.record()
+            for _ in range(a.iters):
+                whole_fwd()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_w = e0.elapsed_time(e1) / a.iters
+        dist.barrier()
+    if rank == 0:
+        res["ms_whole_scene_1gpu"] = round(ms_w, 4)
+        res["speedup_vs_1gpu"] = round(ms_w / ms_sh, 3)
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
