@@ -18,9 +18,12 @@
 
 namespace mvsd {
 
-constexpr int kBpWarps = 8;
-constexpr int kBpThreads = kBpWarps * 32;
-constexpr int kBpVox = 32;            // voxels per CTA
+constexpr int kBpVox = 32;            // voxels per CTA (one 128 B store row per channel)
+// Warps per CTA is a template parameter: more warps = fewer voxels per warp, i.e. a
+// shorter dependent chain (project -> hypotheses -> ballot -> feature gather) per
+// warp and higher occupancy; ncu showed the 8-warp / 4-voxels-per-warp form waiting
+// on exactly that chain (long-scoreboard 4.8-11.9 per issue at 23% occupancy).
+// 16 warps (2 voxels per warp) measured best: 52 -> 37 us fwd, 65 -> 46 us bwd.
 constexpr int kTileStride = 132;      // floats per voxel row of the transpose tile
 
 struct BpParams {
@@ -61,8 +64,8 @@ __device__ __forceinline__ LaneHit lane_test(const BpParams& p, int vi, float X,
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <typename TIn, int G, int MODE, bool CFIRST>
-__global__ void __launch_bounds__(kBpThreads) backproject_fwd_kernel(const BpParams p) {
+template <typename TIn, int G, int MODE, bool CFIRST, int kBpWarps>
+__global__ void __launch_bounds__(kBpWarps * 32) backproject_fwd_kernel(const BpParams p) {
   __shared__ float s_tile[CFIRST ? kBpVox * kTileStride : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = p.C, N = p.N;
@@ -161,8 +164,8 @@ __global__ void __launch_bounds__(kBpThreads) backproject_fwd_kernel(const BpPar
 //   dL/dfeat[i,y,x,:] += weight * g_vol ;  dL/dweight = sum_c g_vol[c] * feat[c]
 //   dL/dpn[i,y,x,j*]  += dL/dweight  (j* = arg max routed by torch.max)
 // ---------------------------------------------------------------------------
-template <typename TIn, int G, int MODE, bool CFIRST>
-__global__ void __launch_bounds__(kBpThreads) backproject_bwd_kernel(const BpParams p) {
+template <typename TIn, int G, int MODE, bool CFIRST, int kBpWarps>
+__global__ void __launch_bounds__(kBpWarps * 32) backproject_bwd_kernel(const BpParams p) {
   __shared__ float s_tile[CFIRST ? kBpVox * kTileStride : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = p.C, N = p.N;
@@ -279,13 +282,13 @@ __global__ void voxel_normalize_kernel(const float* __restrict__ sum, const int3
 // ---------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------
-template <typename TIn, int G, bool BWD>
-static int launch_bp_mode(const BpParams& p, int mode, bool cfirst, cudaStream_t st) {
+template <typename TIn, int G, bool BWD, int WARPS>
+static int launch_bp_warps(const BpParams& p, int mode, bool cfirst, cudaStream_t st) {
   dim3 grid((p.N + kBpVox - 1) / kBpVox);
-#define MVSD_BP_LAUNCH(M, CF)                                                         \
-  do {                                                                                \
-    if (BWD) backproject_bwd_kernel<TIn, G, M, CF><<<grid, kBpThreads, 0, st>>>(p);   \
-    else backproject_fwd_kernel<TIn, G, M, CF><<<grid, kBpThreads, 0, st>>>(p);       \
+#define MVSD_BP_LAUNCH(M, CF)                                                                 \
+  do {                                                                                        \
+    if (BWD) backproject_bwd_kernel<TIn, G, M, CF, WARPS><<<grid, WARPS * 32, 0, st>>>(p);    \
+    else backproject_fwd_kernel<TIn, G, M, CF, WARPS><<<grid, WARPS * 32, 0, st>>>(p);        \
   } while (0)
   if (mode == MVSD_BP_PER_VIEW) MVSD_BP_LAUNCH(MVSD_BP_PER_VIEW, false);
   else if (mode == MVSD_BP_MEAN && cfirst) MVSD_BP_LAUNCH(MVSD_BP_MEAN, true);
@@ -295,6 +298,14 @@ static int launch_bp_mode(const BpParams& p, int mode, bool cfirst, cudaStream_t
 #undef MVSD_BP_LAUNCH
   count_launch();
   return check_launch(BWD ? "backproject_bwd" : "backproject_fwd");
+}
+
+template <typename TIn, int G, bool BWD>
+static int launch_bp_mode(const BpParams& p, int mode, bool cfirst, cudaStream_t st) {
+  const int t = tuning(7);               // tuning key 7: warps per CTA (8, 16, 32); 0 = default
+  if (t == 8) return launch_bp_warps<TIn, G, BWD, 8>(p, mode, cfirst, st);
+  if (t == 32) return launch_bp_warps<TIn, G, BWD, 32>(p, mode, cfirst, st);
+  return launch_bp_warps<TIn, G, BWD, 16>(p, mode, cfirst, st);   // measured best on B200 (fwd 37 us, bwd 46 us)
 }
 
 template <bool BWD>

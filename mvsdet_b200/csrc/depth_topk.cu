@@ -27,7 +27,10 @@ struct TopkParams {
   int raw;   // 1: channel 0 already holds probabilities, channel 1 offsets
 };
 
-template <int DMAX>
+// FAST (backward only): ex2.approx-based exp and approximate division -- the
+// backward needs the probabilities to ~1e-6 relative for the gradient, not the
+// bit pattern that decided the top-k (the indices come from the forward).
+template <int DMAX, bool FAST>
 __device__ __forceinline__ void load_pixel(const TopkParams& p, int v, int pix, float (&prob)[DMAX],
                                            float (&off)[DMAX]) {
   const float* c0 = p.cost + v * p.s_v + pix * p.s_p;
@@ -46,14 +49,15 @@ __device__ __forceinline__ void load_pixel(const TopkParams& p, int v, int pix, 
 #pragma unroll
   for (int d = 0; d < DMAX; ++d) {
     if (d < p.D) {
-      prob[d] = expf(prob[d] - mx);
+      prob[d] = FAST ? __expf(prob[d] - mx) : expf(prob[d] - mx);
       sum += prob[d];
-      off[d] = 1.0f / (1.0f + expf(-off[d]));
+      off[d] = FAST ? __fdividef(1.0f, 1.0f + __expf(-off[d])) : 1.0f / (1.0f + expf(-off[d]));
     }
   }
+  const float inv = FAST ? __fdividef(1.0f, sum) : 0.f;
 #pragma unroll
   for (int d = 0; d < DMAX; ++d)
-    if (d < p.D) prob[d] = prob[d] / sum;
+    if (d < p.D) prob[d] = FAST ? prob[d] * inv : prob[d] / sum;
 }
 
 // depth of plane d with its offset: (d*interval + near) + off*interval, each
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(128) depth_topk_fwd_kernel(const TopkParams p)
   const int v = blockIdx.y;
   if (pix >= p.HW) return;
   float prob[DMAX], off[DMAX];
-  load_pixel<DMAX>(p, v, pix, prob, off);
+  load_pixel<DMAX, false>(p, v, pix, prob, off);
 
   float coding = 0.f;
 #pragma unroll
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(128) depth_topk_bwd_kernel(const TopkParams p)
   const int v = blockIdx.y;
   if (pix >= p.HW) return;
   float prob[DMAX], off[DMAX], gp[DMAX], gs[DMAX];
-  load_pixel<DMAX>(p, v, pix, prob, off);
+  load_pixel<DMAX, true>(p, v, pix, prob, off);
   const float gcod = p.g_coding ? __ldg(p.g_coding + (size_t)v * p.HW + pix) : 0.f;
 #pragma unroll
   for (int d = 0; d < DMAX; ++d) {
@@ -168,7 +172,10 @@ static int check_topk(const char* who, int V, int D, int H, int W, int T) {
 template <bool BWD>
 static int launch_topk(const TopkParams& p, cudaStream_t st) {
   dim3 grid((p.HW + 127) / 128, p.V);
-  if (p.D <= 16) {
+  if (p.D <= 12) {                      // the shipped configs: D = num_monocular_samples = 12
+    if (BWD) depth_topk_bwd_kernel<12><<<grid, 128, 0, st>>>(p);
+    else depth_topk_fwd_kernel<12><<<grid, 128, 0, st>>>(p);
+  } else if (p.D <= 16) {
     if (BWD) depth_topk_bwd_kernel<16><<<grid, 128, 0, st>>>(p);
     else depth_topk_fwd_kernel<16><<<grid, 128, 0, st>>>(p);
   } else if (p.D <= 32) {

@@ -81,6 +81,7 @@ class ScenePipeline:
         self.g_cost_out = torch.empty((v, 2, d, hf, wf), **f32)
         self.geo: Optional[SceneGeometry] = None
         self._host = None
+        self._side = torch.cuda.Stream(device=dev)     # zero-fills of the gradient accumulators
 
     # ------------------------------------------------------------------
     def set_geometry(self, geo: SceneGeometry) -> None:
@@ -147,6 +148,14 @@ class ScenePipeline:
             e1.record()
             timers.setdefault(name, []).append((e0, e1))
 
+        # the two accumulator zero-fills (98 MB + 1 MB) have no producer: they run on a
+        # side stream under the forward kernels and join before the first backward kernel
+        # (a fork/join edge pair once the step is captured into a graph)
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self.g_feat_cl.zero_()
+            self.g_pn.zero_()
         if self.pack_input:
             run("pack", "mvsd_pack_nchw_to_nhwc", self.feature.data_ptr(), self.feat_cl.data_ptr(),
                 fdt, v, c, hf, wf, st)
@@ -164,8 +173,7 @@ class ScenePipeline:
             self.volume_mean.data_ptr(), CHANNELS_FIRST, self.count.data_ptr(), None, None,
             v, c, h, w, t, n, st)
         # ---- backward
-        self.g_feat_cl.zero_()
-        self.g_pn.zero_()
+        cur.wait_stream(self._side)
         run("backproject_bwd", "mvsd_backproject_bwd", self.g_volume_mean.data_ptr(), CHANNELS_FIRST,
             BP_MEAN, self.count.data_ptr(), self.feat_cl.data_ptr(), fdt, hf, wf,
             geo.points.data_ptr(), geo.projection.data_ptr(), self.est_depth.data_ptr(),

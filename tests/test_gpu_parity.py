@@ -192,6 +192,25 @@ def test_pack_unpack_roundtrip():
     assert torch.equal(out, x)
 
 
+@pytest.mark.parametrize("shape", [(2, 7, 5, 9), (1, 66, 13, 70), (3, 256, 60, 80)])
+def test_pack_unpack_ragged_shapes(shape):
+    """64x64 transpose tiles: ragged channel / pixel edges, odd C, multi-tile maps."""
+    from mvsdet_b200 import _lib
+    v, c, h, w = shape
+    x = torch.randn(*shape, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for dt, code in ((torch.float32, 0), (torch.bfloat16, 1)):
+        cl = torch.empty((v, h, w, c), dtype=dt, device="cuda")
+        _lib.call("mvsd_pack_nchw_to_nhwc", x.data_ptr(), cl.data_ptr(), code, v, c, h, w, st)
+        assert torch.equal(cl, x.permute(0, 2, 3, 1).to(dt))
+    cl32 = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.full_like(x, 2.0)
+    _lib.call("mvsd_unpack_nhwc_to_nchw", cl32.data_ptr(), out.data_ptr(), 1, v, c, h, w, st)
+    assert torch.equal(out, x + 2.0)
+    _lib.call("mvsd_unpack_nhwc_to_nchw", cl32.data_ptr(), out.data_ptr(), 0, v, c, h, w, st)
+    assert torch.equal(out, x)
+
+
 def test_errors_are_loud():
     from mvsdet_b200 import ops
     with pytest.raises(ValueError):
