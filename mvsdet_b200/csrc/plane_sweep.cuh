@@ -175,6 +175,49 @@ __device__ __forceinline__ P4 p4fma(P4 a, P4 b, P4 c) {
   return P4{fma2(a.lo, b.lo, c.lo), fma2(a.hi, b.hi, c.hi)};
 }
 
+// ---- tensor memory as a warp-private fp32 accumulator file --------------------
+// 32x32b shape: lane l of warp w touches TMEM lane 32*(w%4)+l, 4 consecutive
+// columns per access; the column index is a run-time value.  Used for per-pixel
+// gradient accumulators that must persist across the plane loop (512 B per pixel
+// per 128 channels) without costing registers or shared memory (= L1 capacity).
+// tools/tmem_probe.cu verifies this usage on the GPU.
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, P4 v) {
+  float a, b, c, d;
+  upk2(v.lo, a, b);
+  upk2(v.hi, c, d);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               :: "r"(taddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ P4 tmem_ld4(uint32_t taddr) {
+  float a, b, c, d;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return P4{pk2(a, b), pk2(c, d)};
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// One warp allocates COLS columns for the CTA and publishes the base through smem;
+// every thread of the CTA must call both functions (they contain CTA barriers).
+template <int COLS>
+__device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t* s_base, int warp) {
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(s_base)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *s_base + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's lane quarter
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free_cta(uint32_t* s_base, int warp) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*s_base), "n"(COLS) : "memory");
+}
+
 // raw (un-converted) 4-channel loads, so the bf16 -> fp32 shift/mask lands next
 // to the packed arithmetic that consumes it
 template <typename T> struct Raw;
@@ -186,6 +229,13 @@ template <> struct Raw<float> {
   static __device__ __forceinline__ float4 ld_stream(const float* p) {
     return __ldcs(reinterpret_cast<const float4*>(p));
   }
+  // read-once stream that must not displace the gathered taps from L1
+  static __device__ __forceinline__ float4 ld_stream_na(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+  }
   static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 };
 template <> struct Raw<__nv_bfloat16> {
@@ -195,6 +245,11 @@ template <> struct Raw<__nv_bfloat16> {
   }
   static __device__ __forceinline__ uint2 ld_stream(const __nv_bfloat16* p) {
     return __ldcs(reinterpret_cast<const uint2*>(p));
+  }
+  static __device__ __forceinline__ uint2 ld_stream_na(const __nv_bfloat16* p) {
+    uint2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
   }
   static __device__ __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
 };

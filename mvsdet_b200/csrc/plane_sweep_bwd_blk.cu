@@ -37,23 +37,6 @@ constexpr int kBTmemCols = kBRun * kBRows * 4;   // 128: 4 fp32 columns per pixe
 constexpr unsigned kNoCell = 0xfffffffeu;
 static_assert(kBTmemCols == 128, "TMEM allocation must be a power of two >= 32 columns");
 
-// ---- tensor memory as a warp-private accumulator file ------------------------
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, P4 v) {
-  float a, b, c, d;
-  upk2(v.lo, a, b);
-  upk2(v.hi, c, d);
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-               :: "r"(taddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ P4 tmem_ld4(uint32_t taddr) {
-  float a, b, c, d;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  return P4{pk2(a, b), pk2(c, d)};
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 __device__ __forceinline__ void red_p4(float* p, P4 v) {
   float a, b, c, d;
   upk2(v.lo, a, b);

@@ -274,13 +274,27 @@ __device__ __forceinline__ void scatter_side_p(float* dst, const P4 (&gw)[G], fl
 
 constexpr int kPrefetchPlanes = 2;
 
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB>
+// TM = true keeps the per-pixel reference-gradient accumulators in tensor memory
+// (kRun * G * 4 columns per CTA) instead of 32 KB of shared memory per CTA: the
+// L1 that shared memory was carved out of goes back to the gathered taps.
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, bool TM>
 __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runp_kernel(const SweepParams p) {
+  constexpr int kCols = kRun * G * 4;
   __shared__ WarpSample s_tab[kRunRows][32];
-  __shared__ P4 s_gref[kRunRows][kRun][G][32];
+  __shared__ P4 s_gref[TM ? 1 : kRunRows][TM ? 1 : kRun][G][32];
+  __shared__ uint32_t s_tmem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const RunCoord c = run_coord<G>(p, warp, lane);
-  if (c.y >= p.H) return;
+  uint32_t tbase = 0;
+  if (TM) tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);
+  auto gref_ld = [&](int i, int g) -> P4 {
+    return TM ? tmem_ld4(tbase + 4u * (uint32_t)(i * G + g)) : s_gref[TM ? 0 : warp][TM ? 0 : i][g][lane];
+  };
+  auto gref_st = [&](int i, int g, P4 v) {
+    if (TM) tmem_st4(tbase + 4u * (uint32_t)(i * G + g), v);
+    else s_gref[TM ? 0 : warp][TM ? 0 : i][g][lane] = v;
+  };
+  if (c.y < p.H) {
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
   const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
@@ -326,7 +340,8 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runp_kernel(const
 #pragma unroll
   for (int i = 0; i < kRun; ++i)
 #pragma unroll
-    for (int g = 0; g < G; ++g) s_gref[warp][i][g][lane] = p4zero();
+    for (int g = 0; g < G; ++g) gref_st(i, g, p4zero());
+  if (TM) tmem_wait_st();
 
   for (int d0 = 0; d0 < p.D; d0 += ppf) {
     __syncwarp();
@@ -335,6 +350,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runp_kernel(const
     const int dend = min(p.D, d0 + ppf);
     for (int d = d0; d < dend; ++d) {
       prefetch_plane(d + kPrefetchPlanes);
+      if (TM) tmem_wait_st();
       P4 open_top[KMAX][G], open_bot[KMAX][G];
       unsigned o_top[KMAX], o_bot[KMAX];
 #pragma unroll
@@ -354,7 +370,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runp_kernel(const
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const bool on = group_on<FULL>(c.c0, g, C);
-          graw[g] = on ? Raw<TG>::ld_stream(g_d + i * C + 128 * g) : Raw<TG>::zero();
+          graw[g] = on ? Raw<TG>::ld_stream_na(g_d + i * C + 128 * g) : Raw<TG>::zero();
           rraw[g] = on ? Raw<TIn>::ld(ref_row + i * C + 128 * g) : Raw<TIn>::zero();
         }
         // all loads of the pixel (gradient, reference, both neighbours' taps) go out
@@ -382,7 +398,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runp_kernel(const
             if (j < k) mu[g] = p4add(mu[g], wv[j][g]);
           mu[g] = p4scale(mu[g], inv_n2);
           gv[g] = p4scale(p4from(graw[g]), two_inv_n2);
-          s_gref[warp][i][g][lane] = p4fma(gv[g], p4sub(ref[g], mu[g]), s_gref[warp][i][g][lane]);
+          gref_st(i, g, p4fma(gv[g], p4sub(ref[g], mu[g]), gref_ld(i, g)));
         }
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
@@ -409,12 +425,17 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runp_kernel(const
       g_d += plane_stride;
     }
   }
+  if (TM) tmem_wait_st();
   float* dst = p.g_feat + ref_off;
   for (int i = 0; i < c.npix; ++i) {
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, s_gref[warp][i][g][lane]);
+    for (int g = 0; g < G; ++g) {
+      const P4 acc = gref_ld(i, g);
+      if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, acc);
+    }
   }
+  }  // c.y < p.H
+  if (TM) tmem_free_cta<kCols>(&s_tmem, warp);
 }
 
 // k in {1,2} only (k*kRun <= 32 samples per plane); other k use the pixel kernel.
@@ -428,12 +449,14 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   if (blocks > 2147483647LL) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_bwd: grid too large");
   dim3 grid((unsigned)blocks);
   const bool full = p.C % (128 * G) == 0;
+  const bool tm = tuning(4) == 0;          // tuning key 4: 0 = TMEM accumulators (default), 2 = shared memory
   const bool minb3 = tuning(4) != 1;       // tuning key 4: 1 = cap at 128 registers (4 CTAs/SM) instead of 168 (3)
   const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel, 3 = packed
 #define MVSD_RUN(KM, GG, FU)                                                              \
   do {                                                                                    \
-    if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
-    else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4><<<grid, kRunThreads, 0, st>>>(p); \
+    if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, false><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4, false><<<grid, kRunThreads, 0, st>>>(p); \
     else sweep_bwd_run_kernel<TIn, TG, KM, GG, FU><<<grid, kRunThreads, 0, st>>>(p);        \
   } while (0)
   if (p.k == 1) {

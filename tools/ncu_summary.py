@@ -37,7 +37,43 @@ WANT = [
 ]
 
 
+KERNEL_KEYS = (("sweep_fwd", "plane_sweep_fwd"), ("sweep_bwd", "plane_sweep_bwd"),
+               ("backproject_fwd", "backproject_fwd"), ("backproject_bwd", "backproject_bwd"),
+               ("depth_topk_fwd", "depth_topk_fwd"), ("depth_topk_bwd", "depth_topk_bwd"),
+               ("unpack_kernel", "unpack"), ("pack_kernel", "pack"), ("prob_norm", "prob_norm_bwd"))
+
+
+def to_bytes(value, unit):
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    return float(value.replace(",", "")) * mult.get(unit, 1)
+
+
+def traffic(paths, out_path):
+    """profiles/traffic.json: per-launch DRAM bytes (read + write) of each kernel,
+    mean over the captured launches -- bench.py's roofline.traffic."""
+    import json
+    acc = {}
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units = rows[0], rows[1]
+        ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        for r in rows[2:]:
+            for frag, key in KERNEL_KEYS:
+                if frag in r[ki]:
+                    acc.setdefault(key, []).append(to_bytes(r[ri], units[ri]) + to_bytes(r[wi], units[wi]))
+                    break
+    res = {k: int(sum(v) / len(v)) for k, v in acc.items()}
+    with open(out_path, "w") as fh:
+        json.dump(res, fh, indent=1, sort_keys=True)
+    print(json.dumps(res))
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--traffic":
+        traffic(sys.argv[3:], sys.argv[2])
+        return
     for path in sys.argv[1:]:
         out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
                              text=True).stdout

@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Wall-clock of the autograd drop-in (MVSDetHotPath forward + backward through
+torch.autograd) per scene, with and without a cached SceneGeometry -- the cost a
+maintainer sees after applying INTEGRATION.md level 1, host work included."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from mvsdet_b200.hotpath import MVSDetHotPath
+from mvsdet_b200.scene import SceneConfig, make_scene
+
+cfg = SceneConfig(n_views=20)
+scene = make_scene(cfg, seed=0)
+dev = torch.device("cuda")
+hot = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
+                    feature_dtype=torch.bfloat16)
+feat = scene["feature"].to(dev).requires_grad_(True)
+cost = scene["cost_out"].to(dev).requires_grad_(True)
+gvar = scene["g_variance"].to(dev)
+gvol = scene["g_volume_mean"].to(dev)
+
+def step(geo=None):
+    res = hot(feat, scene["img_meta"], cost_regularization=lambda var: cost, geometry=geo)
+    torch.autograd.backward([res["variance"], res["volume_mean"]], [gvar, gvol])
+    feat.grad = None; cost.grad = None
+
+out = {}
+for name, geo in (("geometry_every_call", None), ("geometry_cached", hot.geometry(scene["img_meta"], dev))):
+    for _ in range(5):
+        step(geo)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 30
+    for _ in range(n):
+        step(geo)
+    torch.cuda.synchronize()
+    out[name + "_ms"] = round((time.perf_counter() - t0) / n * 1e3, 3)
+t0 = time.perf_counter()
+for _ in range(20):
+    hot.geometry(scene["img_meta"], dev)
+torch.cuda.synchronize()
+out["geometry_host_ms"] = round((time.perf_counter() - t0) / 20 * 1e3, 3)
+print(json.dumps(out))
