@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: depth-plane / view-count / resolution sweep of the
+fused plane-sweep kernels, charting achieved algorithmic GB/s against the
+measured HBM peak.
+
+Views are independent in the sweep, so large configurations are processed in
+view chunks sized to a memory budget (the variance of ONE 480x640x256 view at
+D=64 is 20 GB); the reported time is the sum over chunks, the bytes are the
+algorithmic bytes of the whole configuration (features read once per chunk they
+are needed in + variance written once; backward: g_variance + features read,
+g_feat written).
+
+    python tools/sweep_chart.py --out gpurun_out/sweep_chart.json
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from mvsdet_b200 import ops  # noqa: E402
+from mvsdet_b200.hotpath import MVSDetHotPath  # noqa: E402
+from mvsdet_b200.scene import SceneConfig, make_cameras  # noqa: E402
+import numpy as np  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def run_config(v, d, hf, wf, c, budget_gb, backward, dev):
+    far = 0.2 + 0.4 * d                      # keep the reference's 0.4 m plane spacing
+    cfg = SceneConfig(n_views=v, channels=c, num_depth=d, near_far_range=(0.2, far),
+                      img_shape=(hf * 4 - 1, wf * 4), pad_shape=(hf * 4, wf * 4),
+                      ori_shape=(hf * 16, wf * 16))
+    rng = np.random.default_rng(v * 1000 + d)
+    w2c, intr = make_cameras(cfg, rng)
+    img_meta = dict(lidar2img=dict(extrinsic=[m for m in w2c], intrinsic=intr,
+                                   origin=np.asarray(cfg.origin, dtype=np.float32)),
+                    img_shape=cfg.img_shape, ori_shape=cfg.ori_shape, pad_shape=cfg.pad_shape)
+    hot = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, d, cfg.topk)
+    feat = torch.randn((v, hf, wf, c), device=dev, dtype=torch.float32).to(torch.bfloat16).permute(0, 3, 1, 2)
+    per_view = c * d * hf * wf * 4
+    chunk = max(1, min(v, int(budget_gb * 1e9 // (per_view * (2 if backward else 1)))))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_f = ms_b = 0.0
+    g_feat_total = None
+    for b in range(0, v, chunk):
+        e = min(v, b + chunk)
+        geo = hot.geometry(img_meta, dev, view_slice=slice(b, e))
+        fl = feat.detach().requires_grad_(backward)
+        best = float("inf")
+        for rep in range(4):                                   # best of the warm repetitions (the op allocates its output)
+            var = None
+            e0.record()
+            var = ops.plane_sweep_variance(fl, geo.neighbor_ids, geo.hom, geo.depth_values, ref_begin=b)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = min(best, e0.elapsed_time(e1))
+        ms_f += best
+        finite = bool(torch.isfinite(var[-1, :, -1]).all())
+        if backward:
+            g = torch.empty_like(var).normal_()
+            best = float("inf")
+            for rep in range(3):
+                fl.grad = None
+                e0.record()
+                var.backward(g, retain_graph=True)
+                e1.record()
+                torch.cuda.synchronize()
+                if rep:
+                    best = min(best, e0.elapsed_time(e1))
+            ms_b += best
+            del g
+        del var
+    feat_b = v * c * hf * wf * 2
+    vol_b = v * c * d * hf * wf * 4
+    out = dict(views=v, planes=d, feature_map=[hf, wf], channels=c, view_chunk=chunk,
+               fwd_ms=round(ms_f, 3), fwd_gbs=round((feat_b + vol_b) / ms_f / 1e6, 1), finite=finite)
+    if backward:
+        out.update(bwd_ms=round(ms_b, 3), bwd_gbs=round((vol_b + feat_b + v * c * hf * wf * 4) / ms_b / 1e6, 1))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/sweep_chart.json")
+    ap.add_argument("--budget-gb", type=float, default=24.0)
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    pk = peak()
+    grid = []
+    if a.quick:
+        grid = [(10, 16, 60, 80), (4, 64, 120, 160)]
+    else:
+        for hf, wf in ((60, 80), (120, 160)):
+            for d in (12, 16, 32, 64):
+                for v in (10, 20, 50, 100):
+                    grid.append((v, d, hf, wf))
+        for d in (16, 64):                                      # full-resolution 480x640 feature maps
+            grid.append((10, d, 480, 640))
+    rows = []
+    for v, d, hf, wf in grid:
+        r = run_config(v, d, hf, wf, 256, a.budget_gb, backward=(hf * wf <= 160 * 120), dev=dev)
+        r["fwd_frac_of_hbm_peak"] = round(r["fwd_gbs"] / pk, 3)
+        if "bwd_gbs" in r:
+            r["bwd_frac_of_hbm_peak"] = round(r["bwd_gbs"] / pk, 3)
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+    json.dump(dict(hbm_peak_gbs=pk, rows=rows), open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
