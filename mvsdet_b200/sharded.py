@@ -14,7 +14,9 @@ buffer: they are integers <= V <= 2^24, so the sum is exact.
 
 The FPN feature maps of all V views are resident on every rank (the k=2 pose
 neighbours of a local view may belong to another rank, SURVEY.md 8e caveat 1);
-only the reference-view work is partitioned.
+only the reference-view work is partitioned: a rank packs (fp32 NCHW -> channels-last
+bf16/fp32) just its own block plus the few neighbour views outside it ("halo"), and
+the neighbour ids are re-based onto that compact buffer.
 
 The partition / packing / all-reduce helpers are device-agnostic host logic and
 are exercised with a world-size-2 gloo group on CPU (tests/test_sharded_cpu.py);
@@ -22,13 +24,39 @@ are exercised with a world-size-2 gloo group on CPU (tests/test_sharded_cpu.py);
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional, Tuple
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
-__all__ = ["partition_views", "pack_partials", "unpack_partials", "allreduce_partials",
-           "ShardedSceneForward"]
+__all__ = ["partition_views", "halo_views", "pack_partials", "unpack_partials",
+           "allreduce_partials", "LocalGeometry", "ShardedSceneForward"]
+
+
+def halo_views(neighbor_ids: torch.Tensor, begin: int, end: int) -> Tuple[List[int], torch.Tensor]:
+    """Views a rank must hold to sweep reference views [begin, end): the block
+    itself followed by the neighbour views outside it, ascending.  Returns
+    (global view ids in local order, neighbour ids re-based to local indices
+    [V_local,k] int32).  Pure host logic (tested on CPU)."""
+    nbr = neighbor_ids.to(torch.int64).cpu()
+    own = list(range(begin, end))
+    extra = sorted(set(int(x) for x in nbr.reshape(-1).tolist()) - set(own))
+    order = own + extra
+    lut = {g: i for i, g in enumerate(order)}
+    local = torch.tensor([[lut[int(x)] for x in row] for row in nbr.tolist()],
+                         dtype=torch.int32).reshape(nbr.shape[0], nbr.shape[1] if nbr.dim() > 1 else 0)
+    return order, local
+
+
+@dataclass
+class LocalGeometry:
+    """A rank's slice of the scene parameter block plus its halo bookkeeping."""
+    geo: object                    # SceneGeometry of reference views [begin, end)
+    views: List[int]               # global view ids held locally (block first, then halo)
+    neighbor_ids_local: torch.Tensor   # [V_local,k] int32 on the device, indices into ``views``
+    begin: int
+    end: int
 
 
 def partition_views(n_views: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -95,14 +123,77 @@ class ShardedSceneForward:
             return dist.get_rank(self.group), dist.get_world_size(self.group)
         return 0, 1
 
-    def local_geometry(self, img_meta: dict, n_views: int, device):
-        """This rank's slice of the per-scene parameter block (host work, ~2 ms;
-        a caller that revisits a scene passes it back in as ``geometry``)."""
+    def local_geometry(self, img_meta: dict, n_views: int, device) -> Optional[LocalGeometry]:
+        """This rank's slice of the per-scene parameter block and its halo (host
+        work, ~2 ms; a caller that revisits a scene passes it back in as
+        ``geometry``)."""
         rank, world = self._world()
         begin, end = partition_views(n_views, world, rank)
         if end <= begin:
             return None
-        return self.hot.geometry(img_meta, device, view_slice=slice(begin, end))
+        geo = self.hot.geometry(img_meta, device, view_slice=slice(begin, end))
+        views, nbr_local = halo_views(geo.neighbor_ids_host, begin, end)
+        return LocalGeometry(geo=geo, views=views, neighbor_ids_local=nbr_local.to(device),
+                             begin=begin, end=end)
+
+    def _pack_local(self, feature: torch.Tensor, lg: LocalGeometry) -> torch.Tensor:
+        """fp32 NCHW [V,C,H,W] -> channels-last buffer of the views in ``lg.views``
+        (contiguous runs of views go through one transpose launch each)."""
+        from . import _lib, ops
+        v, c, h, w = feature.shape
+        dt = self.hot.feature_dtype
+        if feature.dtype != torch.float32 or not feature.is_contiguous():
+            return ops.pack_features(feature[lg.views], dt)       # already channels-last / bf16 inputs
+        out = torch.empty((len(lg.views), h, w, c), dtype=dt, device=feature.device)
+        code = _lib.BF16 if dt == torch.bfloat16 else _lib.F32
+        st = torch.cuda.current_stream().cuda_stream
+        i = 0
+        while i < len(lg.views):
+            j = i
+            while j + 1 < len(lg.views) and lg.views[j + 1] == lg.views[j] + 1:
+                j += 1
+            _lib.call("mvsd_pack_nchw_to_nhwc", feature[lg.views[i]].data_ptr(), out[i].data_ptr(), code,
+                      j - i + 1, c, h, w, st)
+            i = j + 1
+        return out.permute(0, 3, 1, 2)
+
+    def local_partials(self, feature: torch.Tensor, img_meta: dict, cost_net: Callable,
+                       geometry: Optional[LocalGeometry] = None, rank_world: Optional[Tuple[int, int]] = None):
+        """This rank's contribution before the collective: (volume_sum logical
+        [C,N], count int32 [N], (begin, end)).  ``rank_world`` overrides the
+        process group (used by the single-GPU tests to play every rank)."""
+        from . import ops
+        hot = self.hot
+        rank, world = rank_world or self._world()
+        v_all = feature.shape[0]
+        begin, end = partition_views(v_all, world, rank)
+        c = feature.shape[1]
+        nx, ny, nz = hot.n_voxels
+        n = nx * ny * nz
+        dev = feature.device
+        if end > begin:
+            lg = geometry
+            if lg is None:
+                geo = hot.geometry(img_meta, dev, view_slice=slice(begin, end))
+                views, nbr_local = halo_views(geo.neighbor_ids_host, begin, end)
+                lg = LocalGeometry(geo, views, nbr_local.to(dev), begin, end)
+            geo = lg.geo
+            feat_cl = self._pack_local(feature, lg)            # block + halo only
+            variance = ops.plane_sweep_variance(feat_cl, lg.neighbor_ids_local, geo.hom,
+                                                geo.depth_values, out_dtype=hot.variance_dtype,
+                                                ref_begin=0)
+            cost_out = cost_net(variance)
+            _, _, est_depth, est_dens, est_idx, _ = hot.hypotheses(cost_out)
+            vol_sum, count = ops.backproject_aggregate(
+                feat_cl[:end - begin], geo.points, geo.projection, est_depth, est_dens,
+                hot.voxel_size[2], geo.height, geo.width, mode="sum",
+                channels_first=hot.channels_first_volume)
+        else:                                   # more ranks than views: contribute zeros
+            shape = (c, n) if hot.channels_first_volume else (n, c)
+            vol_sum = torch.zeros(shape, dtype=torch.float32, device=dev)
+            vol_sum = vol_sum if hot.channels_first_volume else vol_sum.t()
+            count = torch.zeros(n, dtype=torch.int32, device=dev)
+        return vol_sum, count, (begin, end)
 
     def __call__(self, feature: torch.Tensor, img_meta: dict,
                  cost_regularization: Optional[Callable] = None, geometry=None) -> Dict[str, torch.Tensor]:
@@ -111,28 +202,10 @@ class ShardedSceneForward:
         cost_net = cost_regularization or hot.cost_regularization
         if cost_net is None:
             raise ValueError("a cost_regularization callable is required (mvsdet.py:470)")
-        rank, world = self._world()
-        v_all = feature.shape[0]
-        begin, end = partition_views(v_all, world, rank)
-        feat_cl = ops.pack_features(feature, hot.feature_dtype)
-        c = feat_cl.shape[1]
+        c = feature.shape[1]
         nx, ny, nz = hot.n_voxels
         n = nx * ny * nz
-        dev = feature.device
-        if end > begin:
-            geo = geometry or hot.geometry(img_meta, dev, view_slice=slice(begin, end))
-            variance = hot.variance(feat_cl, geo, ref_begin=begin)
-            cost_out = cost_net(variance)
-            _, _, est_depth, est_dens, est_idx, _ = hot.hypotheses(cost_out)
-            vol_sum, count = ops.backproject_aggregate(
-                feat_cl[begin:end], geo.points, geo.projection, est_depth, est_dens,
-                hot.voxel_size[2], geo.height, geo.width, mode="sum",
-                channels_first=hot.channels_first_volume)
-        else:                                   # more ranks than views: contribute zeros
-            shape = (c, n) if hot.channels_first_volume else (n, c)
-            vol_sum = torch.zeros(shape, dtype=torch.float32, device=dev)
-            vol_sum = vol_sum if hot.channels_first_volume else vol_sum.t()
-            count = torch.zeros(n, dtype=torch.int32, device=dev)
+        vol_sum, count, (begin, end) = self.local_partials(feature, img_meta, cost_net, geometry)
         buf = pack_partials(vol_sum.detach(), count)
         allreduce_partials(buf, self.group)
         vol_sum, count = unpack_partials(buf, c, n, hot.channels_first_volume)

@@ -183,6 +183,36 @@ def test_view_sharded_partials_match_whole_scene(full_scene, hot, shards):
     _close(mean.reshape(-1), whole["volume_mean"].reshape(-1), "sharded volume_mean", rtol=1e-5, atol_scale=1e-6)
 
 
+@pytest.mark.parametrize("world", [1, 4])
+def test_sharded_forward_class_with_halo_packing(full_scene, hot, world):
+    """ShardedSceneForward.local_partials played for every rank on one GPU (block +
+    halo packing, re-based neighbour ids) against the whole-scene forward."""
+    from mvsdet_b200 import ops, sharded
+    scene, cfg = full_scene, full_scene["cfg"]
+    dev = torch.device("cuda")
+    feat = scene["feature"].to(dev)
+    cost = scene["cost_out"].to(dev)
+    whole = hot(feat, scene["img_meta"], cost_regularization=lambda var: cost)
+    runner = sharded.ShardedSceneForward(hot)
+    c, n = cfg.channels, int(np.prod(cfg.n_voxels))
+    total = None
+    for rank in range(world):
+        b, e = sharded.partition_views(cfg.n_views, world, rank)
+        vol, cnt, rng = runner.local_partials(feat, scene["img_meta"], lambda var: cost[b:e],
+                                              rank_world=(rank, world))
+        assert rng == (b, e)
+        buf = sharded.pack_partials(vol, cnt)
+        total = buf if total is None else total + buf
+    vol_sum, count = sharded.unpack_partials(total, c, n)
+    mean = ops.voxel_normalize(vol_sum.contiguous(), count)
+    assert torch.equal(count, whole["count"])
+    _close(mean.reshape(-1), whole["volume_mean"].reshape(-1), "sharded class volume_mean", rtol=1e-5, atol_scale=1e-6)
+    if world == 1:
+        out = runner(feat, scene["img_meta"], cost_regularization=lambda var: cost)
+        assert torch.equal(out["count"], whole["count"])
+        _close(out["volume_mean"].reshape(-1), whole["volume_mean"].reshape(-1), "sharded __call__", rtol=1e-5, atol_scale=1e-6)
+
+
 def test_arkit_shaped_full_size_subset():
     """configs[3]: per-view intrinsics, near/far [0.5, 5.5], 40 views (train)."""
     from mvsdet_b200 import ops

@@ -2,7 +2,8 @@
 partitioning, packing and a REAL world-size-2 all-reduce over gloo.  The
 per-rank partial voxel sums come from the oracle (test infrastructure) -- on a
 GPU box the same partials come from mvsd_backproject_fwd(MVSD_BP_SUM), which
-tests/test_gpu_parity.py::test_view_sharded_partials_match_whole_scene covers.
+tests/test_gpu_fullsize.py (test_view_sharded_partials_match_whole_scene,
+test_sharded_forward_class_with_halo_packing) covers.
 """
 import os
 import socket
@@ -29,6 +30,18 @@ def test_partition_views_covers_everything_once():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         sharded.partition_views(4, 2, 2)
+
+
+def test_halo_views_rebases_neighbours():
+    nbr = torch.tensor([[3, 5], [2, 6], [4, 9], [5, 0]])          # reference views 4..7 of a 10-view scene
+    order, local = sharded.halo_views(nbr, 4, 8)
+    assert order[:4] == [4, 5, 6, 7] and order[4:] == [0, 2, 3, 9]
+    assert local.dtype == torch.int32 and tuple(local.shape) == (4, 2)
+    for r in range(4):
+        for j in range(2):
+            assert order[int(local[r, j])] == int(nbr[r, j])
+    order, local = sharded.halo_views(torch.zeros((3, 0), dtype=torch.int64), 0, 3)   # k = 0
+    assert order == [0, 1, 2] and tuple(local.shape) == (3, 0)
 
 
 def test_pack_unpack_roundtrip_both_memory_orders():

@@ -76,7 +76,7 @@ def main():
     res = {"views": cfg.n_views, "world": world, "ms_sharded_forward": round(ms_sh, 4),
            "scenes_per_s_sharded": round(1e3 / ms_sh, 2), "feature_dtype": a.feature_dtype,
            "allreduce_bytes": int(out_sh["volume_mean"].numel() * 4 + out_sh["count"].numel() * 4),
-           "neighbour_features": "replicated on every rank"}
+           "neighbour_features": "fp32 FPN maps of all views resident on every rank; each rank packs its block + halo views only"}
     if rank == 0:
         ms_w, out_w = timed(whole_fwd) if world == 1 else (None, None)
     if world > 1:
