@@ -22,13 +22,15 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvsdet_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
-SOURCES = ("capi.cu", "pack.cu", "plane_sweep_fwd.cu", "plane_sweep_bwd.cu", "plane_sweep_bwd_run.cu", "plane_sweep_bwd_blk.cu",
+SOURCES = ("capi.cu", "pack.cu", "plane_sweep_fwd.cu", "plane_sweep_bwd.cu", "plane_sweep_bwd_run.cu", "plane_sweep_bwd_blk.cu", "plane_sweep_bwd_rows.cu",
            "depth_topk.cu",
            "backproject.cu")
 HEADERS = (os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "plane_sweep.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "mvsdet_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# experiment builds only (e.g. MVSD_EXTRA_NVCC_FLAGS="-DMVSD_KRUN=16"); part of the object digest
+NVCC_FLAGS += os.environ.get("MVSD_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -137,6 +137,7 @@ static int launch_bwd_k(SweepParams& p, cudaStream_t st) {
 
 int launch_bwd_run(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st);
 int launch_bwd_blk(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st);
+int launch_bwd_rows(SweepParams& p, int rows, int feat_dtype, int g_dtype, cudaStream_t st);
 
 }  // namespace mvsd
 
@@ -157,9 +158,13 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // tuning key 5: 0/unset = packed run-merging kernel (k <= 2), 1 = pixel kernel,
   // 2 = scalar run-merging kernel, 4 = block-merging kernel (TMEM + row cache; fewer
-  // REDs but more instructions: measured slower)
+  // REDs but more instructions: measured slower), 5 / 6 = two- / four-row
+  // blocks with two pending columns per source row (plane_sweep_bwd_rows.cu: 25-35% fewer
+  // RED bytes, 1.7x the instructions: measured slower)
   const int variant = tuning(5);
   if ((k == 1 || k == 2) && variant == 4) return launch_bwd_blk(p, feat_dtype, g_dtype, st);
+  if ((k == 1 || k == 2) && (variant == 5 || variant == 6))
+    return launch_bwd_rows(p, variant == 5 ? 2 : 4, feat_dtype, g_dtype, st);
   if ((k == 1 || k == 2) && variant != 1) return launch_bwd_run(p, feat_dtype, g_dtype, st);
   if (feat_dtype == MVSD_F32 && g_dtype == MVSD_F32) return launch_bwd_k<float, float, false>(p, st);
   if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_F32)

@@ -13,7 +13,10 @@
 
 namespace mvsd {
 
-constexpr int kRun = 8;                    // pixels per warp run
+#ifndef MVSD_KRUN
+#define MVSD_KRUN 8
+#endif
+constexpr int kRun = MVSD_KRUN;            // pixels per warp run
 constexpr int kRunRows = 4;                // rows (= warps) per CTA
 constexpr int kRunThreads = kRunRows * 32;
 constexpr unsigned kNoTap = 0xfffffffeu;   // "nothing pending"
@@ -221,7 +224,13 @@ __global__ void __launch_bounds__(kRunThreads, 4) sweep_bwd_run_kernel(const Swe
 //     flight per SM), now they are L2 hits and cost no registers;
 //   * neighbour base pointers are pinned in registers.
 // ---------------------------------------------------------------------------
+#ifdef MVSD_EXP_NORED
+__constant__ int c_exp_nored;      // experiment: measure the kernel with the neighbour REDs suppressed
+#endif
 __device__ __forceinline__ void red_add_p4(float* p, P4 v) {
+#ifdef MVSD_EXP_NORED
+  if (c_exp_nored) return;
+#endif
   float a, b, c, d;
   upk2(v.lo, a, b);
   upk2(v.hi, c, d);
@@ -452,6 +461,10 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   const bool tm = tuning(4) == 0;          // tuning key 4: 0 = TMEM accumulators (default), 2 = shared memory
   const bool minb3 = tuning(4) != 1;       // tuning key 4: 1 = cap at 128 registers (4 CTAs/SM) instead of 168 (3)
   const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel, 3 = packed
+#ifdef MVSD_EXP_NORED
+  { const int flag = tuning(6); cudaMemcpyToSymbolAsync(c_exp_nored, &flag, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
+#endif
+#if MVSD_KRUN == 8
 #define MVSD_RUN(KM, GG, FU)                                                              \
   do {                                                                                    \
     if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
@@ -459,6 +472,10 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
     else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4, false><<<grid, kRunThreads, 0, st>>>(p); \
     else sweep_bwd_run_kernel<TIn, TG, KM, GG, FU><<<grid, kRunThreads, 0, st>>>(p);        \
   } while (0)
+#else   // experiment builds with longer runs: TMEM variant only (the smem accumulators exceed 48 KB)
+#define MVSD_RUN(KM, GG, FU) \
+  sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p)
+#endif
   if (p.k == 1) {
     if (G == 2) { if (full) MVSD_RUN(1, 2, true); else MVSD_RUN(1, 2, false); }
     else { if (full) MVSD_RUN(1, 1, true); else MVSD_RUN(1, 1, false); }

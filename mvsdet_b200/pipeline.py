@@ -82,6 +82,8 @@ class ScenePipeline:
         self.geo: Optional[SceneGeometry] = None
         self._host = None
         self._side = torch.cuda.Stream(device=dev)     # zero-fills of the gradient accumulators
+        self._aux = torch.cuda.Stream(device=dev, priority=-1)   # the small kernels, see step()
+        self.overlap_small = True
 
     # ------------------------------------------------------------------
     def set_geometry(self, geo: SceneGeometry) -> None:
@@ -148,10 +150,17 @@ class ScenePipeline:
             e1.record()
             timers.setdefault(name, []).append((e0, e1))
 
-        # the two accumulator zero-fills (98 MB + 1 MB) have no producer: they run on a
-        # side stream under the forward kernels and join before the first backward kernel
-        # (a fork/join edge pair once the step is captured into a graph)
+        # Three streams (fork/join edges once the step is captured into a graph):
+        #   cur    pack -> sweep fwd -> sweep bwd -> unpack      (the two 1.2 GB streaming kernels)
+        #   _aux   top-k fwd -> voxels fwd -> voxels bwd -> pn bwd -> top-k bwd
+        #          small latency-bound kernels (2-3 waves, L2-resident operands) that depend only
+        #          on pack; they run under the sweep kernels at higher stream priority.  The two
+        #          backward kernels accumulate into g_feat_cl with commutative REDs.
+        #   _side  zero-fills of the gradient accumulators (98 MB + 1 MB), no producer
+        # With ``timers`` the kernels run back to back on ``cur`` so each can be timed alone.
         cur = torch.cuda.current_stream()
+        overlap = timers is None and self.overlap_small
+        aux = self._aux if overlap else cur
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             self.g_feat_cl.zero_()
@@ -159,35 +168,47 @@ class ScenePipeline:
         if self.pack_input:
             run("pack", "mvsd_pack_nchw_to_nhwc", self.feature.data_ptr(), self.feat_cl.data_ptr(),
                 fdt, v, c, hf, wf, st)
-        run("plane_sweep_fwd", "mvsd_plane_sweep_fwd", self.feat_cl.data_ptr(), fdt,
-            geo.neighbor_ids.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(),
-            self.variance.data_ptr(), vdt, CHANNELS_LAST, v, c, d, hf, wf, k, 0, st)
+        if overlap:
+            aux.wait_stream(cur)
+        else:
+            run("plane_sweep_fwd", "mvsd_plane_sweep_fwd", self.feat_cl.data_ptr(), fdt,
+                geo.neighbor_ids.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(),
+                self.variance.data_ptr(), vdt, CHANNELS_LAST, v, c, d, hf, wf, k, 0, st)
         sc = self.cost_out.stride()
-        run("depth_topk_fwd", "mvsd_depth_topk_fwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2],
-            sc[4], self.prob_volume.data_ptr(), self.off_pred.data_ptr(), self.est_depth.data_ptr(),
-            self.est_dens.data_ptr(), self.est_idx.data_ptr(), self.depth_coding.data_ptr(),
-            float(cfg.near_far_range[0]), float(cfg.depth_interval), 0, v, d, hf, wf, t, st)
-        run("backproject_fwd", "mvsd_backproject_fwd", self.feat_cl.data_ptr(), fdt, hf, wf,
-            geo.points.data_ptr(), geo.projection.data_ptr(), self.est_depth.data_ptr(),
-            self.est_dens.data_ptr(), sv, sy, sx, s_t, float(cfg.voxel_size[2]), BP_MEAN,
-            self.volume_mean.data_ptr(), CHANNELS_FIRST, self.count.data_ptr(), None, None,
-            v, c, h, w, t, n, st)
-        # ---- backward
-        cur.wait_stream(self._side)
-        run("backproject_bwd", "mvsd_backproject_bwd", self.g_volume_mean.data_ptr(), CHANNELS_FIRST,
-            BP_MEAN, self.count.data_ptr(), self.feat_cl.data_ptr(), fdt, hf, wf,
-            geo.points.data_ptr(), geo.projection.data_ptr(), self.est_depth.data_ptr(),
-            self.est_dens.data_ptr(), sv, sy, sx, s_t, float(cfg.voxel_size[2]),
-            self.g_feat_cl.data_ptr(), self.g_pn.data_ptr(), v, c, h, w, t, n, st)
-        run("prob_norm_bwd", "mvsd_prob_norm_bwd", self.est_dens.data_ptr(), self.g_pn.data_ptr(),
-            self.g_est_dens.data_ptr(), sv, sy, sx, s_t, v, h, w, t, st)
-        run("depth_topk_bwd", "mvsd_depth_topk_bwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2],
-            sc[4], self.est_idx.data_ptr(), None, None, None, self.g_est_dens.data_ptr(), None,
-            self.g_cost_out.data_ptr(), float(cfg.near_far_range[0]), float(cfg.depth_interval), 0,
-            v, d, hf, wf, t, st)
+        with torch.cuda.stream(aux):
+            sa = aux.cuda_stream
+            run("depth_topk_fwd", "mvsd_depth_topk_fwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2],
+                sc[4], self.prob_volume.data_ptr(), self.off_pred.data_ptr(), self.est_depth.data_ptr(),
+                self.est_dens.data_ptr(), self.est_idx.data_ptr(), self.depth_coding.data_ptr(),
+                float(cfg.near_far_range[0]), float(cfg.depth_interval), 0, v, d, hf, wf, t, sa)
+            run("backproject_fwd", "mvsd_backproject_fwd", self.feat_cl.data_ptr(), fdt, hf, wf,
+                geo.points.data_ptr(), geo.projection.data_ptr(), self.est_depth.data_ptr(),
+                self.est_dens.data_ptr(), sv, sy, sx, s_t, float(cfg.voxel_size[2]), BP_MEAN,
+                self.volume_mean.data_ptr(), CHANNELS_FIRST, self.count.data_ptr(), None, None,
+                v, c, h, w, t, n, sa)
+            # ---- backward
+            aux.wait_stream(self._side)
+            run("backproject_bwd", "mvsd_backproject_bwd", self.g_volume_mean.data_ptr(), CHANNELS_FIRST,
+                BP_MEAN, self.count.data_ptr(), self.feat_cl.data_ptr(), fdt, hf, wf,
+                geo.points.data_ptr(), geo.projection.data_ptr(), self.est_depth.data_ptr(),
+                self.est_dens.data_ptr(), sv, sy, sx, s_t, float(cfg.voxel_size[2]),
+                self.g_feat_cl.data_ptr(), self.g_pn.data_ptr(), v, c, h, w, t, n, sa)
+            run("prob_norm_bwd", "mvsd_prob_norm_bwd", self.est_dens.data_ptr(), self.g_pn.data_ptr(),
+                self.g_est_dens.data_ptr(), sv, sy, sx, s_t, v, h, w, t, sa)
+            run("depth_topk_bwd", "mvsd_depth_topk_bwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2],
+                sc[4], self.est_idx.data_ptr(), None, None, None, self.g_est_dens.data_ptr(), None,
+                self.g_cost_out.data_ptr(), float(cfg.near_far_range[0]), float(cfg.depth_interval), 0,
+                v, d, hf, wf, t, sa)
+        if overlap:
+            run("plane_sweep_fwd", "mvsd_plane_sweep_fwd", self.feat_cl.data_ptr(), fdt,
+                geo.neighbor_ids.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(),
+                self.variance.data_ptr(), vdt, CHANNELS_LAST, v, c, d, hf, wf, k, 0, st)
+            cur.wait_stream(self._side)
         run("plane_sweep_bwd", "mvsd_plane_sweep_bwd", self.g_variance.data_ptr(), vdt, CHANNELS_LAST,
             self.feat_cl.data_ptr(), fdt, geo.neighbor_ids.data_ptr(), geo.hom.data_ptr(),
             geo.depth_values.data_ptr(), self.g_feat_cl.data_ptr(), v, c, d, hf, wf, k, 0, st)
+        if overlap:
+            cur.wait_stream(aux)
         run("unpack", "mvsd_unpack_nhwc_to_nchw", self.g_feat_cl.data_ptr(), self.g_feature.data_ptr(),
             0, v, c, hf, wf, st)
 
