@@ -89,6 +89,45 @@ def compute_projection(img_meta: dict, stride: int) -> torch.Tensor:
     return torch.stack(out)
 
 
+def projection_vectorized(intr_t: torch.Tensor, extr: torch.Tensor, ratio: float) -> torch.Tensor:
+    """Same values as :func:`compute_projection`, bit for bit, without the Python
+    loop over views (0.7 ms -> 0.05 ms at V=20).  ATen's CPU ``mm`` for a 3x3 @ 3x4
+    product accumulates each output as an FMA chain in k order (checked against the
+    loop on 120 seeded scenes, tests/test_geometry_cpu.py); the batched ``bmm`` does
+    NOT round the same way, so the chain is spelled out: the products of two fp32
+    values are exact in fp64, one rounding per step."""
+    v = extr.shape[0]
+    k3 = (intr_t[:, :3, :3] if intr_t.dim() == 3 else intr_t[:3, :3].unsqueeze(0).expand(v, 3, 3)).clone()
+    k3[:, :2] /= ratio
+    a = k3.numpy().astype(np.float64)            # [V,3,3]
+    b = extr[:, :3].numpy().astype(np.float64)   # [V,3,4]
+    acc = (a[:, :, 0:1] * b[:, 0:1, :]).astype(np.float32)
+    for kk in (1, 2):
+        acc = (a[:, :, kk:kk + 1] * b[:, kk:kk + 1, :] + acc.astype(np.float64)).astype(np.float32)
+    return torch.from_numpy(acc)
+
+
+_STATIC_CACHE: dict = {}
+
+
+def static_geometry(n_voxels, voxel_size, origin, near_far_range, num_depth: int, n_views: int, device):
+    """Voxel centres and depth planes depend only on the detector configuration
+    (mvsdet.py:222-225, :1316-1327): built once per (config, device) and kept on
+    the device instead of being rebuilt and re-uploaded (307 KB) for every scene."""
+    key = (tuple(int(n) for n in n_voxels), tuple(float(x) for x in voxel_size),
+           tuple(float(x) for x in np.asarray(origin).reshape(-1)),
+           tuple(float(x) for x in near_far_range), int(num_depth), int(n_views), str(device))
+    hit = _STATIC_CACHE.get(key)
+    if hit is None:
+        points = get_points(n_voxels, voxel_size, origin)
+        dvals = torch.as_tensor(depth_values_for(near_far_range, num_depth)).unsqueeze(0).repeat(n_views, 1)
+        hit = (points.to(device), dvals.to(device))
+        if len(_STATIC_CACHE) > 64:
+            _STATIC_CACHE.clear()
+        _STATIC_CACHE[key] = hit
+    return hit
+
+
 def get_points(n_voxels, voxel_size, origin) -> torch.Tensor:
     """Reference: get_points, mvsdet.py:1316-1327 -> [3,nx,ny,nz] fp32."""
     n_voxels = torch.as_tensor(n_voxels)
@@ -141,19 +180,24 @@ def scene_geometry(img_meta: dict, *, stride: int, near_far_range, num_depth: in
     nbr = get_nearest_pose_ids(c2w, c2w, k, maskself=True)            # [V,k] int64
     ref_proj, nei_projs = collect_proj(w2c, k_feat, nbr)
     if k > 0:
-        hom = torch.stack([homography_params(np_, ref_proj) for np_ in nei_projs], dim=1)
+        # src_proj @ inverse(ref_proj) (module.py:116-118) per neighbour; the inverse of the
+        # reference projections is the same tensor for every neighbour, so it is taken once
+        inv_ref = torch.inverse(ref_proj)
+        m = torch.stack([torch.matmul(np_, inv_ref) for np_ in nei_projs], dim=1)     # [V,k,4,4]
+        hom = torch.cat((m[:, :, :3, :3].reshape(v_all, k, 9), m[:, :, :3, 3]), dim=2).contiguous()
     else:
         hom = torch.zeros(v_all, 0, 12)
-    dvals = torch.as_tensor(depth_values_for(near_far_range, num_depth)).unsqueeze(0).repeat(v_all, 1)
-    projection = compute_projection(img_meta, stride)
-    points = get_points(n_voxels, voxel_size, img_meta["lidar2img"]["origin"])
+    projection = projection_vectorized(intr, w2c, ratio)
+    dev = torch.device(device)
     if view_slice is not None:
-        nbr, hom, dvals, projection = nbr[view_slice], hom[view_slice], dvals[view_slice], projection[view_slice]
+        nbr, hom, projection = nbr[view_slice], hom[view_slice], projection[view_slice]
+    v = nbr.shape[0]
+    points, dplanes = static_geometry(n_voxels, voxel_size, img_meta["lidar2img"]["origin"],
+                                      near_far_range, num_depth, v, dev)
 
     parts = [nbr.to(torch.int32).reshape(-1).view(torch.float32) if nbr.numel() else torch.zeros(0),
-             hom.reshape(-1), dvals.reshape(-1), projection.reshape(-1), points.reshape(-1)]
+             hom.reshape(-1), projection.reshape(-1)]
     sizes = [p.numel() for p in parts]
-    dev = torch.device(device)
     if dev.type == "cuda":
         staging = torch.empty(sum(sizes), dtype=torch.float32, pin_memory=True)
         torch.cat(parts, out=staging)
@@ -161,13 +205,12 @@ def scene_geometry(img_meta: dict, *, stride: int, near_far_range, num_depth: in
     else:
         blob = torch.cat(parts)
     o = np.cumsum([0] + sizes)
-    v = nbr.shape[0]
     return SceneGeometry(
         neighbor_ids=blob[o[0]:o[1]].view(torch.int32).view(v, k),
         hom=blob[o[1]:o[2]].view(v, k, 12),
-        depth_values=blob[o[2]:o[3]].view(v, num_depth),
-        projection=blob[o[3]:o[4]].view(v, 3, 4),
-        points=blob[o[4]:o[5]].view(3, *[int(n) for n in n_voxels]),
+        depth_values=dplanes,
+        projection=blob[o[2]:o[3]].view(v, 3, 4),
+        points=points,
         neighbor_ids_host=nbr,
         height=img_meta["img_shape"][0] // stride,
         width=img_meta["img_shape"][1] // stride,
