@@ -325,6 +325,37 @@ def run_own_arm(args, cfg, cfg_json):
         except Exception:
             pass
 
+    # ---- the autograd drop-in (MVSDetHotPath + torch.autograd, host geometry every call):
+    # what a maintainer gets from INTEGRATION.md level 1, wall clock incl. host work
+    module_api = None
+    if world == 1:
+        hot = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
+                            stride=cfg.stride, feature_dtype=feat_dtype)
+        m_feat = p0.feature.detach().clone().requires_grad_(True)
+        m_cost = p0.cost_out.detach().clone().requires_grad_(True)
+        m_gvar = p0.g_variance.permute(0, 4, 1, 2, 3)       # channels_last_3d view, as cuDNN returns it
+        m_gvol = p0.g_volume_mean.view(cfg.channels, *cfg.n_voxels)
+
+        def module_step():
+            res = hot(m_feat, host_scene["img_meta"], cost_regularization=lambda var: m_cost)
+            torch.autograd.backward([res["variance"], res["volume_mean"]], [m_gvar, m_gvol])
+            m_feat.grad = None
+            m_cost.grad = None
+
+        for _ in range(5):
+            module_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_mod = 30
+        for _ in range(n_mod):
+            module_step()
+        torch.cuda.synchronize()
+        ms_mod = (time.perf_counter() - t0) / n_mod * 1e3
+        module_api = {"value": 1e3 / ms_mod, "unit": UNIT, "ms_per_scene": round(ms_mod, 4), "steps": n_mod,
+                      "what": "MVSDetHotPath forward + torch.autograd backward, scene geometry "
+                              "recomputed on the host every call, caching allocator, no CUDA graph"}
+        del hot, m_feat, m_cost
+
     if rank == 0:
         cpu_line = None
         if world == 1 and not args.no_cpu_baseline:
@@ -347,6 +378,8 @@ def run_own_arm(args, cfg, cfg_json):
             "cuda_graph": use_graph,
             "roofline": roofline, "kernels": kernels,
         }
+        if module_api is not None:
+            line["module_api"] = module_api
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
         print(json.dumps(line), flush=True)

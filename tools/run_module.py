@@ -16,7 +16,9 @@ hot = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_de
                     feature_dtype=torch.bfloat16)
 feat = scene["feature"].to(dev).requires_grad_(True)
 cost = scene["cost_out"].to(dev).requires_grad_(True)
-gvar = scene["g_variance"].to(dev)
+# the gradient arrives in the variance's own memory format (channels_last_3d), as cuDNN's
+# Conv3d backward returns it for a channels_last_3d input
+gvar = scene["g_variance"].to(dev).contiguous(memory_format=torch.channels_last_3d)
 gvol = scene["g_volume_mean"].to(dev)
 
 def step(geo=None):
@@ -41,3 +43,12 @@ for _ in range(20):
 torch.cuda.synchronize()
 out["geometry_host_ms"] = round((time.perf_counter() - t0) / 20 * 1e3, 3)
 print(json.dumps(out))
+
+# where the host time goes: torch profiler table of one step (top entries)
+if os.environ.get("MVSD_PROFILE"):
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            step(None)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25))
