@@ -79,7 +79,7 @@ class MVSDetHotPath(nn.Module):
         already channels_last / bf16).  Returns a dict with
           volume_mean [C,nx,ny,nz], valid [1,nx,ny,nz] (float count, as
           extract_feat returns it, mvsdet.py:698), count int32 [N],
-          variance, prob_volume, off_pred, est_depth, est_densities, est_idx,
+          variance, prob_volume, off_pred, est_depth, est_densities, est_idx, opacity,
           depth_coding [V,1,h,w] -- the reference's intermediates."""
         cost_net = cost_regularization or self.cost_regularization
         if cost_net is None:
@@ -96,5 +96,8 @@ class MVSDetHotPath(nn.Module):
         return dict(volume_mean=volume_mean, valid=count.view(1, nx, ny, nz).float(), count=count,
                     variance=variance, prob_volume=prob, off_pred=off, est_depth=est_depth,
                     est_densities=est_dens, est_idx=est_idx,
+                    # NVS branch: opacity = max_d prob_volume (mvsdet.py:579) is the top-1
+                    # hypothesis probability, bit for bit
+                    opacity=est_dens[:, 0],
                     depth_coding=coding[:, :geo.height, :geo.width].unsqueeze(1),
                     neighbor_ids=geo.neighbor_ids_host)

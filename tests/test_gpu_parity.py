@@ -70,6 +70,8 @@ def test_chain_fp32_vs_reference_golden(case, channels_first):
     for key in ("variance", "prob_volume", "off_pred", "est_depth", "est_densities",
                 "depth_coding", "volume_mean"):
         _close(res[key], gold[key], f"{case}:{key}")
+    # NVS opacity (mvsdet.py:579) = max_d prob_volume = the top-1 hypothesis probability
+    assert torch.equal(res["opacity"], res["prob_volume"].max(dim=1)[0])
     for key in ("g_feature_from_variance", "g_feature_from_voxels"):
         _close(res[key], gold[key], f"{case}:{key}")
     # with T == 1 the normalised probability is identically 1 and its gradient
