@@ -156,8 +156,8 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   p.g_feat = g_feat;
   p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // tuning key 5: 0/unset = packed run-merging kernel (k <= 2), 1 = pixel kernel,
-  // 2 = scalar run-merging kernel, 4 = block-merging kernel (TMEM + row cache; fewer
+  // tuning key 5: 0/unset = lean packed run-merging kernel (k <= 2), 1 = pixel kernel,
+  // 2 = scalar run-merging kernel, 3 = first packed run-merging kernel, 4 = block-merging kernel (TMEM + row cache; fewer
   // REDs but more instructions: measured slower), 5 / 6 = two- / four-row
   // blocks with two pending columns per source row (plane_sweep_bwd_rows.cu: 25-35% fewer
   // RED bytes, 1.7x the instructions: measured slower)

@@ -447,6 +447,200 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runp_kernel(const
   if (TM) tmem_free_cta<kCols>(&s_tmem, warp);
 }
 
+// ---------------------------------------------------------------------------
+// Lean variant (default since round 1d).  ncu's per-instruction counts on the packed
+// kernel above: 335 warp instructions per pixel-plane of which 81 are register moves
+// (MOV / IMAD.MOV / CS2R at the joins of "zero, then blend if the sample is valid" and of
+// the merge-or-flush branches) and 63 are control flow.  Same algorithm, restructured so
+// that nothing is merged at a join:
+//   * the pixel body is instantiated per validity pattern of the two samples (a
+//     warp-uniform 4-way branch): an absent sample has no loads, no blend, no zeroed
+//     vector and leaves the pending taps alone (a later mismatch or the end of the run
+//     flushes them);
+//   * the scatter keeps one invariant -- "the pending accumulator is zero unless it
+//     matches the next left tap" -- so the mismatch arm only issues a RED and zeroes the
+//     pending registers in place, and the left tap is always fma(gw, w_left, pending).
+// ---------------------------------------------------------------------------
+template <int KMAX, int G>
+struct RunPending {
+  P4 top[KMAX][G], bot[KMAX][G];
+  unsigned id_top[KMAX], id_bot[KMAX];
+};
+
+template <int G, bool FULL>
+__device__ __forceinline__ void side_q(float* dst, const P4 (&gw)[G], float w_left, float w_right,
+                                       unsigned p_left, unsigned p_right, unsigned& open_id,
+                                       P4 (&open)[G], int c0, int C) {
+  const bool match = open_id == p_left;
+  const u64 wl = pk2(w_left, w_left), wr = pk2(w_right, w_right);
+  P4 a[G];
+  if (match) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = p4fma(gw[g], wl, open[g]);
+  } else {
+    if (open_id != kNoTap) red_group_p<G, FULL>(dst, open_id, open, c0, C);
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = p4scale(gw[g], wl);
+  }
+  if (match || w_left != 0.f) red_group_p<G, FULL>(dst, p_left, a, c0, C);
+#pragma unroll
+  for (int g = 0; g < G; ++g) open[g] = p4scale(gw[g], wr);
+  open_id = w_right != 0.f ? p_right : kNoTap;
+}
+
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1>
+__device__ __forceinline__ void pixel_q(RunPending<KMAX, G>& pend, const WarpSample& s0,
+                                        const WarpSample& s1, const TG* __restrict__ gp,
+                                        const TIn* __restrict__ rp, const TIn* const (&nsrc)[KMAX],
+                                        float* const (&ndst)[KMAX], uint32_t taddr, u64 inv_n2,
+                                        u64 two_inv_n2, int c0, int C) {
+  typename Raw<TG>::type graw[G];
+  typename Raw<TIn>::type rraw[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const bool on = group_on<FULL>(c0, g, C);
+    graw[g] = on ? Raw<TG>::ld_stream_na(gp + 128 * g) : Raw<TG>::zero();
+    rraw[g] = on ? Raw<TIn>::ld(rp + 128 * g) : Raw<TIn>::zero();
+  }
+  RawTaps<TIn, G> t0, t1;
+  if (V0) load_taps<TIn, G, FULL>(nsrc[0], s0, c0, C, t0);
+  if (V1) load_taps<TIn, G, FULL>(nsrc[KMAX - 1], s1, c0, C, t1);
+  P4 w0[G], w1[G], gw0[G], gw1[G];
+  if (V0) blend_taps<TIn, G>(t0, s0, w0);
+  if (V1) blend_taps<TIn, G>(t1, s1, w1);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const P4 ref = p4from(rraw[g]);
+    P4 mu = ref;
+    if (V0) mu = p4add(mu, w0[g]);
+    if (V1) mu = p4add(mu, w1[g]);
+    mu = p4scale(mu, inv_n2);
+    const P4 gv = p4scale(p4from(graw[g]), two_inv_n2);
+    const uint32_t ta = taddr + 4u * (uint32_t)g;
+    tmem_st4(ta, p4fma(gv, p4sub(ref, mu), tmem_ld4(ta)));
+    if (V0) gw0[g] = p4mul(gv, p4sub(w0[g], mu));
+    if (V1) gw1[g] = p4mul(gv, p4sub(w1[g], mu));
+  }
+  if (V0) {
+    side_q<G, FULL>(ndst[0], gw0, s0.w00, s0.w01, s0.p00, s0.p01, pend.id_top[0], pend.top[0], c0, C);
+    side_q<G, FULL>(ndst[0], gw0, s0.w10, s0.w11, s0.p10, s0.p11, pend.id_bot[0], pend.bot[0], c0, C);
+  }
+  if (V1) {
+    side_q<G, FULL>(ndst[KMAX - 1], gw1, s1.w00, s1.w01, s1.p00, s1.p01, pend.id_top[KMAX - 1],
+                    pend.top[KMAX - 1], c0, C);
+    side_q<G, FULL>(ndst[KMAX - 1], gw1, s1.w10, s1.w11, s1.p10, s1.p11, pend.id_bot[KMAX - 1],
+                    pend.bot[KMAX - 1], c0, C);
+  }
+}
+
+// requires p.k == KMAX (the launcher instantiates KMAX = k for k in {1, 2})
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB>
+__global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const SweepParams p) {
+  constexpr int kCols = kRun * G * 4;
+  __shared__ WarpSample s_tab[kRunRows][32];
+  __shared__ uint32_t s_tmem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RunCoord c = run_coord<G>(p, warp, lane);
+  const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);
+  if (c.y < p.H) {
+    const int C = p.C, HW = p.H * p.W;
+    const TIn* feat = static_cast<const TIn*>(p.feat);
+    const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const TIn* ref_row = feat + ref_off;
+    const size_t plane_stride = (size_t)HW * C;
+    const TG* g_d = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const bool one_chunk = p.slices == 1;
+    const unsigned pf_bytes = (unsigned)((one_chunk ? (size_t)c.npix * C : (size_t)min(128 * G, C - (c.c0 - 4 * lane))) *
+                                         sizeof(TG)) & ~15u;
+    const TG* pf_base = g_d - 4 * lane;
+    const bool pf_ok = pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
+                       ((plane_stride * sizeof(TG)) & 15) == 0;
+    auto prefetch_plane = [&](int d) {
+      if (!pf_ok || d >= p.D) return;
+      const TG* q = pf_base + (size_t)d * plane_stride;
+      if (one_chunk) {
+        if (lane == 0) prefetch_l2(q, pf_bytes);
+      } else if (lane < c.npix) {
+        prefetch_l2(q + (size_t)lane * C, pf_bytes);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < kPrefetchPlanes; ++d) prefetch_plane(d);
+
+    const TIn* nsrc[KMAX];
+    float* ndst[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+    }
+    const float inv_n = 1.0f / (float)(KMAX + 1);
+    const u64 inv_n2 = pk2(inv_n, inv_n);
+    const u64 two_inv_n2 = pk2(2.0f * inv_n, 2.0f * inv_n);
+    constexpr int spp = kRun * KMAX;
+    constexpr int ppf = 32 / spp > 0 ? 32 / spp : 1;
+
+#pragma unroll
+    for (int q = 0; q < kRun * G; ++q) tmem_st4(tbase + 4u * (uint32_t)q, p4zero());
+    tmem_wait_st();
+
+    for (int d0 = 0; d0 < p.D; d0 += ppf) {
+      __syncwarp();
+      fill_run_samples(s_tab[warp], p, c, d0, ppf, lane);
+      __syncwarp();
+      const int dend = min(p.D, d0 + ppf);
+      for (int d = d0; d < dend; ++d) {
+        prefetch_plane(d + kPrefetchPlanes);
+        tmem_wait_st();
+        RunPending<KMAX, G> pend;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          pend.id_top[j] = pend.id_bot[j] = kNoTap;
+#pragma unroll
+          for (int g = 0; g < G; ++g) pend.top[j][g] = pend.bot[j][g] = p4zero();
+        }
+        const WarpSample* tab = s_tab[warp] + (d - d0) * spp;
+#pragma unroll 1
+        for (int i = 0; i < c.npix; ++i) {
+          const WarpSample s0 = tab[i * KMAX];
+          const WarpSample s1 = tab[i * KMAX + (KMAX - 1)];
+          const bool v0 = s0.p00 != kNoSample;
+          const bool v1 = KMAX == 2 && s1.p00 != kNoSample;
+          const TG* gp = g_d + i * C;
+          const TIn* rp = ref_row + i * C;
+          const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
+          if (v0 && v1)
+            pixel_q<TIn, TG, KMAX, G, FULL, true, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C);
+          else if (v0)
+            pixel_q<TIn, TG, KMAX, G, FULL, true, false>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C);
+          else if (v1)
+            pixel_q<TIn, TG, KMAX, G, FULL, false, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C);
+          else
+            pixel_q<TIn, TG, KMAX, G, FULL, false, false>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C);
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          flush_open_p<G, FULL>(ndst[j], pend.id_top[j], pend.top[j], c.c0, C);
+          flush_open_p<G, FULL>(ndst[j], pend.id_bot[j], pend.bot[j], c.c0, C);
+        }
+        g_d += plane_stride;
+      }
+    }
+    tmem_wait_st();
+    float* dst = p.g_feat + ref_off;
+    for (int i = 0; i < c.npix; ++i) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const P4 acc = tmem_ld4(tbase + 4u * (uint32_t)(i * G + g));
+        if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, acc);
+      }
+    }
+  }
+  tmem_free_cta<kCols>(&s_tmem, warp);
+}
+
 // k in {1,2} only (k*kRun <= 32 samples per plane); other k use the pixel kernel.
 template <typename TIn, typename TG>
 static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
@@ -461,13 +655,15 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   const bool tm = tuning(4) == 0;          // tuning key 4: 0 = TMEM accumulators (default), 2 = shared memory
   const bool minb3 = tuning(4) != 1;       // tuning key 4: 1 = cap at 128 registers (4 CTAs/SM) instead of 168 (3)
   const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel, 3 = packed
+  const bool lean = tuning(5) == 0 && tuning(4) == 0;   // default: lean packed kernel (sweep_bwd_runq); tuning 5=3: sweep_bwd_runp
 #ifdef MVSD_EXP_NORED
   { const int flag = tuning(6); cudaMemcpyToSymbolAsync(c_exp_nored, &flag, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
 #endif
 #if MVSD_KRUN == 8
 #define MVSD_RUN(KM, GG, FU)                                                              \
   do {                                                                                    \
-    if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
+    if (lean) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, false><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4, false><<<grid, kRunThreads, 0, st>>>(p); \
     else sweep_bwd_run_kernel<TIn, TG, KM, GG, FU><<<grid, kRunThreads, 0, st>>>(p);        \
