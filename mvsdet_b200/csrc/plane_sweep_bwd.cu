@@ -160,7 +160,8 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   // 2 = scalar run-merging kernel, 3 = first packed run-merging kernel, 4 = block-merging kernel (TMEM + row cache; fewer
   // REDs but more instructions: measured slower), 5 / 6 = two- / four-row
   // blocks with two pending columns per source row (plane_sweep_bwd_rows.cu: 25-35% fewer
-  // RED bytes, 1.7x the instructions: measured slower)
+  // RED bytes, 1.7x the instructions: measured slower), 8 = row hand-off between the warps
+  // of a CTA (sweep_bwd_runh: -29% RED bytes, +50% instructions incl. mbarrier waits: slower)
   const int variant = tuning(5);
   if ((k == 1 || k == 2) && variant == 4) return launch_bwd_blk(p, feat_dtype, g_dtype, st);
   if ((k == 1 || k == 2) && (variant == 5 || variant == 6))

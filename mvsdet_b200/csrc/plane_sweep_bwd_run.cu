@@ -471,21 +471,34 @@ template <int G, bool FULL>
 __device__ __forceinline__ void side_q(float* dst, const P4 (&gw)[G], float w_left, float w_right,
                                        unsigned p_left, unsigned p_right, unsigned& open_id,
                                        P4 (&open)[G], int c0, int C) {
-  const bool match = open_id == p_left;
   const u64 wl = pk2(w_left, w_left), wr = pk2(w_right, w_right);
   P4 a[G];
-  if (match) {
+  if (open_id == p_left) {                 // source x advanced by one: pending + left leave as one RED
 #pragma unroll
     for (int g = 0; g < G; ++g) a[g] = p4fma(gw[g], wl, open[g]);
+    red_group_p<G, FULL>(dst, p_left, a, c0, C);
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = p4scale(gw[g], wr);
+    open_id = w_right != 0.f ? p_right : kNoTap;
+  } else if (open_id == p_right && w_right != 0.f) {   // source x did not advance: right joins the pending tap
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = p4fma(gw[g], wr, open[g]);
+    if (w_left != 0.f) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) a[g] = p4scale(gw[g], wl);
+      red_group_p<G, FULL>(dst, p_left, a, c0, C);
+    }
   } else {
     if (open_id != kNoTap) red_group_p<G, FULL>(dst, open_id, open, c0, C);
+    if (w_left != 0.f) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) a[g] = p4scale(gw[g], wl);
+      for (int g = 0; g < G; ++g) a[g] = p4scale(gw[g], wl);
+      red_group_p<G, FULL>(dst, p_left, a, c0, C);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = p4scale(gw[g], wr);
+    open_id = w_right != 0.f ? p_right : kNoTap;
   }
-  if (match || w_left != 0.f) red_group_p<G, FULL>(dst, p_left, a, c0, C);
-#pragma unroll
-  for (int g = 0; g < G; ++g) open[g] = p4scale(gw[g], wr);
-  open_id = w_right != 0.f ? p_right : kNoTap;
 }
 
 template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1>
@@ -641,6 +654,310 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
   tmem_free_cta<kCols>(&s_tmem, warp);
 }
 
+// ---------------------------------------------------------------------------
+// Row-handoff variant (tuning key 5 = 8).  The lean kernel is bound by the RED stream
+// (3.6 GB against a 5.7 TB/s ceiling): a further cut has to merge across image rows.
+// The four warps of a CTA own four consecutive rows of the same 8-pixel run; the bottom
+// taps of row r and the top taps of row r+1 are usually the same two source pixels.
+// When they are (decided identically by both warps from the shared sample tables), warp
+// r does not scatter its bottom contribution: it hands the two weighted vectors to warp
+// r+1 through a double-buffered shared-memory slot (mbarrier full/empty pair, 32
+// arrivals each), and warp r+1 adds them to its own top contribution before its
+// merge-or-flush step.  Replay (tools/red_merge_sim.py): 3.5 -> 2.7 GB of RED payload.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+// side_q for pre-weighted contributions (left / right vectors), used by the receiving
+// side of a hand-off.
+template <int G, bool FULL>
+__device__ __forceinline__ void side_c(float* dst, const P4 (&cl)[G], const P4 (&cr)[G], bool nz_left,
+                                       bool nz_right, unsigned p_left, unsigned p_right,
+                                       unsigned& open_id, P4 (&open)[G], int c0, int C) {
+  P4 a[G];
+  if (open_id == p_left) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = p4add(cl[g], open[g]);
+    red_group_p<G, FULL>(dst, p_left, a, c0, C);
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = cr[g];
+    open_id = nz_right ? p_right : kNoTap;
+  } else if (open_id == p_right && nz_right) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = p4add(cr[g], open[g]);
+    if (nz_left) red_group_p<G, FULL>(dst, p_left, cl, c0, C);
+  } else {
+    if (open_id != kNoTap) red_group_p<G, FULL>(dst, open_id, open, c0, C);
+    if (nz_left) red_group_p<G, FULL>(dst, p_left, cl, c0, C);
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = cr[g];
+    open_id = nz_right ? p_right : kNoTap;
+  }
+}
+
+template <int G>
+struct HandoffSlot {                 // one stage: left and right weighted vectors, lane-private columns
+  P4 v[2][G][32];
+};
+
+// One neighbour's scatter with the hand-off protocol.  send: give the bottom side to the
+// row below; recv: take the row above's bottom side into this row's top side.
+template <int G, bool FULL>
+__device__ __forceinline__ void scatter_h(float* dst, const P4 (&gw)[G], const WarpSample& s,
+                                          unsigned& id_top, P4 (&top)[G], unsigned& id_bot,
+                                          P4 (&bot)[G], bool send, HandoffSlot<G>* out_slot,
+                                          unsigned long long* out_full, unsigned long long* out_empty,
+                                          unsigned& h_out, bool recv, float up_w10, float up_w11,
+                                          HandoffSlot<G>* in_slot, unsigned long long* in_full,
+                                          unsigned long long* in_empty, unsigned& h_in, int lane,
+                                          int c0, int C) {
+  // bottom side first: an early hand-off unblocks the warp below
+  if (send) {
+    const unsigned h = h_out++;
+    const unsigned stg = h & 1u, ph = (h >> 1) & 1u;
+    mbar_wait(out_empty + stg, ph ^ 1u);
+    const u64 w10 = pk2(s.w10, s.w10), w11 = pk2(s.w11, s.w11);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      out_slot[stg].v[0][g][lane] = p4scale(gw[g], w10);
+      out_slot[stg].v[1][g][lane] = p4scale(gw[g], w11);
+    }
+    mbar_arrive(out_full + stg);
+  } else {
+    side_q<G, FULL>(dst, gw, s.w10, s.w11, s.p10, s.p11, id_bot, bot, c0, C);
+  }
+  if (recv) {
+    const unsigned h = h_in++;
+    const unsigned stg = h & 1u, ph = (h >> 1) & 1u;
+    mbar_wait(in_full + stg, ph);
+    P4 cl[G], cr[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cl[g] = in_slot[stg].v[0][g][lane];
+      cr[g] = in_slot[stg].v[1][g][lane];
+    }
+    mbar_arrive(in_empty + stg);
+    const u64 w00 = pk2(s.w00, s.w00), w01 = pk2(s.w01, s.w01);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cl[g] = p4fma(gw[g], w00, cl[g]);
+      cr[g] = p4fma(gw[g], w01, cr[g]);
+    }
+    side_c<G, FULL>(dst, cl, cr, s.w00 != 0.f || up_w10 != 0.f, s.w01 != 0.f || up_w11 != 0.f, s.p00,
+                    s.p01, id_top, top, c0, C);
+  } else {
+    side_q<G, FULL>(dst, gw, s.w00, s.w01, s.p00, s.p01, id_top, top, c0, C);
+  }
+}
+
+// requires p.k == KMAX
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB>
+__global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const SweepParams p) {
+  constexpr int kCols = kRun * G * 4;
+  __shared__ WarpSample s_tab[kRunRows][32];
+  __shared__ __align__(16) HandoffSlot<G> s_slot[kRunRows - 1][KMAX][2];
+  __shared__ __align__(8) unsigned long long s_full[kRunRows - 1][KMAX][2];
+  __shared__ __align__(8) unsigned long long s_empty[kRunRows - 1][KMAX][2];
+  __shared__ uint32_t s_tmem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RunCoord c = run_coord<G>(p, warp, lane);
+  if (threadIdx.x < (kRunRows - 1) * KMAX * 2) {
+    mbar_init(&s_full[0][0][0] + threadIdx.x, 32);
+    mbar_init(&s_empty[0][0][0] + threadIdx.x, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);     // contains the CTA barriers
+  const bool active = c.y < p.H;
+  const int C = p.C, HW = p.H * p.W;
+  const TIn* feat = static_cast<const TIn*>(p.feat);
+  const int yy = active ? c.y : 0;
+  const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)yy * p.W + c.x0) * C + c.c0;
+  const TIn* ref_row = feat + ref_off;
+  const size_t plane_stride = (size_t)HW * C;
+  const TG* g_d = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)yy * p.W + c.x0) * C + c.c0;
+  const bool one_chunk = p.slices == 1;
+  const unsigned pf_bytes = (unsigned)((one_chunk ? (size_t)c.npix * C : (size_t)min(128 * G, C - (c.c0 - 4 * lane))) *
+                                       sizeof(TG)) & ~15u;
+  const TG* pf_base = g_d - 4 * lane;
+  const bool pf_ok = active && pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
+                     ((plane_stride * sizeof(TG)) & 15) == 0;
+  auto prefetch_plane = [&](int d) {
+    if (!pf_ok || d >= p.D) return;
+    const TG* q = pf_base + (size_t)d * plane_stride;
+    if (one_chunk) {
+      if (lane == 0) prefetch_l2(q, pf_bytes);
+    } else if (lane < c.npix) {
+      prefetch_l2(q + (size_t)lane * C, pf_bytes);
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kPrefetchPlanes; ++d) prefetch_plane(d);
+
+  const TIn* nsrc[KMAX];
+  float* ndst[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+    nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+    ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+    asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+  }
+  const float inv_n = 1.0f / (float)(KMAX + 1);
+  const u64 inv_n2 = pk2(inv_n, inv_n);
+  const u64 two_inv_n2 = pk2(2.0f * inv_n, 2.0f * inv_n);
+  constexpr int spp = kRun * KMAX;
+  constexpr int ppf = 32 / spp > 0 ? 32 / spp : 1;
+  const int wdn = min(warp + 1, kRunRows - 1), wup = max(warp - 1, 0);
+  const int bo = min(warp, kRunRows - 2), bi = max(warp - 1, 0);     // boundary below / above this row
+  unsigned h_out[KMAX], h_in[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) h_out[j] = h_in[j] = 0u;
+
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < kRun * G; ++q) tmem_st4(tbase + 4u * (uint32_t)q, p4zero());
+    tmem_wait_st();
+  }
+
+  for (int d0 = 0; d0 < p.D; d0 += ppf) {
+    __syncthreads();                       // every warp is done with the previous tables
+    if (active) {
+      fill_run_samples(s_tab[warp], p, c, d0, ppf, lane);
+    } else {
+      WarpSample none;
+      none.w00 = none.w01 = none.w10 = none.w11 = 0.f;
+      none.p00 = none.p01 = none.p10 = none.p11 = kNoSample;
+      s_tab[warp][lane] = none;
+    }
+    __syncthreads();
+    if (!active) continue;
+    const int dend = min(p.D, d0 + ppf);
+    for (int d = d0; d < dend; ++d) {
+      prefetch_plane(d + kPrefetchPlanes);
+      tmem_wait_st();
+      RunPending<KMAX, G> pend;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        pend.id_top[j] = pend.id_bot[j] = kNoTap;
+#pragma unroll
+        for (int g = 0; g < G; ++g) pend.top[j][g] = pend.bot[j][g] = p4zero();
+      }
+      const int toff = (d - d0) * spp;
+      const WarpSample* tab = s_tab[warp] + toff;
+      const WarpSample* tab_dn = s_tab[wdn] + toff;
+      const WarpSample* tab_up = s_tab[wup] + toff;
+#pragma unroll 1
+      for (int i = 0; i < c.npix; ++i) {
+        WarpSample sm[KMAX];
+        bool val[KMAX], send[KMAX], recv[KMAX];
+        float uw10[KMAX], uw11[KMAX];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          sm[j] = tab[i * KMAX + j];
+          val[j] = sm[j].p00 != kNoSample;
+          any |= val[j];
+          send[j] = recv[j] = false;
+          uw10[j] = uw11[j] = 0.f;
+          if (val[j]) {
+            if (warp + 1 < kRunRows) {
+              const WarpSample& dn = tab_dn[i * KMAX + j];
+              send[j] = dn.p00 != kNoSample && dn.p00 == sm[j].p10 && dn.p01 == sm[j].p11;
+            }
+            if (warp > 0) {
+              const WarpSample& up = tab_up[i * KMAX + j];
+              recv[j] = up.p00 != kNoSample && up.p10 == sm[j].p00 && up.p11 == sm[j].p01;
+              uw10[j] = up.w10;
+              uw11[j] = up.w11;
+            }
+          }
+        }
+        const TG* gp = g_d + i * C;
+        const TIn* rp = ref_row + i * C;
+        typename Raw<TG>::type graw[G];
+        typename Raw<TIn>::type rraw[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const bool on = group_on<FULL>(c.c0, g, C);
+          graw[g] = on ? Raw<TG>::ld_stream_na(gp + 128 * g) : Raw<TG>::zero();
+          rraw[g] = on ? Raw<TIn>::ld(rp + 128 * g) : Raw<TIn>::zero();
+        }
+        RawTaps<TIn, G> traw[KMAX];
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+          if (val[j]) load_taps<TIn, G, FULL>(nsrc[j], sm[j], c.c0, C, traw[j]);
+        P4 wv[KMAX][G], gw[KMAX][G];
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          if (val[j]) {
+            blend_taps<TIn, G>(traw[j], sm[j], wv[j]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) wv[j][g] = p4zero();
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const P4 ref = p4from(rraw[g]);
+          P4 mu = ref;
+#pragma unroll
+          for (int j = 0; j < KMAX; ++j) mu = p4add(mu, wv[j][g]);
+          mu = p4scale(mu, inv_n2);
+          const P4 gv = p4scale(p4from(graw[g]), two_inv_n2);
+          const uint32_t ta = tbase + 4u * (uint32_t)(i * G + g);
+          tmem_st4(ta, p4fma(gv, p4sub(ref, mu), tmem_ld4(ta)));
+#pragma unroll
+          for (int j = 0; j < KMAX; ++j) gw[j][g] = p4mul(gv, p4sub(wv[j][g], mu));
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          if (!val[j]) continue;
+          scatter_h<G, FULL>(ndst[j], gw[j], sm[j], pend.id_top[j], pend.top[j], pend.id_bot[j],
+                             pend.bot[j], send[j], s_slot[bo][j], s_full[bo][j], s_empty[bo][j],
+                             h_out[j], recv[j], uw10[j], uw11[j], s_slot[bi][j], s_full[bi][j],
+                             s_empty[bi][j], h_in[j], lane, c.c0, C);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        flush_open_p<G, FULL>(ndst[j], pend.id_top[j], pend.top[j], c.c0, C);
+        flush_open_p<G, FULL>(ndst[j], pend.id_bot[j], pend.bot[j], c.c0, C);
+      }
+      g_d += plane_stride;
+    }
+  }
+  if (active) {
+    tmem_wait_st();
+    float* dst = p.g_feat + ref_off;
+    for (int i = 0; i < c.npix; ++i) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const P4 acc = tmem_ld4(tbase + 4u * (uint32_t)(i * G + g));
+        if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, acc);
+      }
+    }
+  }
+  tmem_free_cta<kCols>(&s_tmem, warp);
+}
+
 // k in {1,2} only (k*kRun <= 32 samples per plane); other k use the pixel kernel.
 template <typename TIn, typename TG>
 static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
@@ -662,7 +979,8 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
 #if MVSD_KRUN == 8
 #define MVSD_RUN(KM, GG, FU)                                                              \
   do {                                                                                    \
-    if (lean) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
+    if (tuning(5) == 8) sweep_bwd_runh_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (lean) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, false><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4, false><<<grid, kRunThreads, 0, st>>>(p); \

@@ -240,12 +240,13 @@ def test_single_view_scene_variance_is_zero():
     assert float(var.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 8])
 @pytest.mark.parametrize("case", ["scannet_tiny", "two_views", "wide_c"])
 def test_plane_sweep_bwd_variants(case, variant):
     """Every opt-in plane-sweep backward (mvsd_set_tuning key 5: 1 pixel kernel,
     2 scalar run kernel, 3 first packed run kernel, 4 block-merging, 5/6 two-/four-row blocks with two
-    pending columns) must give the reference gradient, like the default."""
+    pending columns, 8 row hand-off through shared-memory slots + mbarriers) must give
+    the reference gradient, like the default."""
     from mvsdet_b200 import _lib
     scene, gold = load_golden(case)
     old = _lib.set_tuning(5, variant)

@@ -74,6 +74,17 @@ def one_slot(state, l, r, cnt):       # plane_sweep_bwd_run.cu scatter_side_p
     state[0] = r if r >= 0 else NO
 
 
+def one_slot_stay(state, l, r, cnt):   # plane_sweep_bwd_run.cu side_q (default kernel)
+    if state[0] == l and l >= 0:
+        cnt[0] += 1
+        state[0] = r if r >= 0 else NO
+    elif state[0] == r and r >= 0:
+        cnt[0] += int(l >= 0)
+    else:
+        cnt[0] += int(state[0] >= 0) + int(l >= 0)
+        state[0] = r if r >= 0 else NO
+
+
 def two_slot(st, l, r, cnt):          # plane_sweep_bwd_rows.cu side_add
     L, R = st
     if l == L and r == R:
@@ -90,7 +101,9 @@ def two_slot(st, l, r, cnt):          # plane_sweep_bwd_rows.cu side_add
 def replay(T, rows, slots, run=8):
     V, k, D, H, W, _ = T.shape
     cnt = [0]
-    add = one_slot if slots == 1 else two_slot
+    add = {1: one_slot, 2: two_slot, "stay": one_slot_stay}[slots]
+    flush_on_empty = slots == 1
+    slots = 2 if slots == 2 else 1
     for v in range(V):
         for j in range(k):
             for d in range(D):
@@ -103,7 +116,7 @@ def replay(T, rows, slots, run=8):
                             for n, r in enumerate(rr):
                                 a = t[r, x]
                                 if (a < 0).all():
-                                    if slots == 1:      # the run kernel flushes on an empty sample
+                                    if flush_on_empty:  # the first run kernels flush on an empty sample
                                         for s in (sides[n], sides[n + 1]):
                                             cnt[0] += int(s[0] >= 0)
                                             s[0] = NO
@@ -140,6 +153,8 @@ def main():
     print(f"samples {samples}, with any tap inside {(T >= 0).any(-1).mean():.3f}, "
           f"unmerged {(T >= 0).sum() * kb:.2f} GB")
     print(f"run kernel (1 row, 1 pending column): {replay(T, 1, 1) * kb:.2f} GB")
+    print(f"lean run kernel (+ right tap joins a pending tap when x does not advance): "
+          f"{replay(T, 1, 'stay') * kb:.2f} GB")
     for rows in (1, 2, 4):
         print(f"{rows}-row blocks, 2 pending columns:     {replay(T, rows, 2) * kb:.2f} GB"
               f"   (ideal {distinct(T, rows, 8, 1) * kb:.2f} GB)")
