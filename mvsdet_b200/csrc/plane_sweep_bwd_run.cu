@@ -501,12 +501,128 @@ __device__ __forceinline__ void side_q(float* dst, const P4 (&gw)[G], float w_le
   }
 }
 
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1>
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+// side_q for pre-weighted contributions (left / right vectors), used by the receiving
+// side of a hand-off.
+template <int G, bool FULL>
+__device__ __forceinline__ void side_c(float* dst, const P4 (&cl)[G], const P4 (&cr)[G], bool nz_left,
+                                       bool nz_right, unsigned p_left, unsigned p_right,
+                                       unsigned& open_id, P4 (&open)[G], int c0, int C) {
+  P4 a[G];
+  if (open_id == p_left) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = p4add(cl[g], open[g]);
+    red_group_p<G, FULL>(dst, p_left, a, c0, C);
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = cr[g];
+    open_id = nz_right ? p_right : kNoTap;
+  } else if (open_id == p_right && nz_right) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = p4add(cr[g], open[g]);
+    if (nz_left) red_group_p<G, FULL>(dst, p_left, cl, c0, C);
+  } else {
+    if (open_id != kNoTap) red_group_p<G, FULL>(dst, open_id, open, c0, C);
+    if (nz_left) red_group_p<G, FULL>(dst, p_left, cl, c0, C);
+#pragma unroll
+    for (int g = 0; g < G; ++g) open[g] = cr[g];
+    open_id = nz_right ? p_right : kNoTap;
+  }
+}
+
+template <int G>
+struct HandoffSlot {                 // one stage: left and right weighted vectors, lane-private columns
+  P4 v[2][G][32];
+};
+
+// One neighbour's scatter with the hand-off protocol.  send: give the bottom side to the
+// row below; recv: take the row above's bottom side into this row's top side.
+template <int G, bool FULL>
+__device__ __forceinline__ void scatter_h(float* dst, const P4 (&gw)[G], const WarpSample& s,
+                                          unsigned& id_top, P4 (&top)[G], unsigned& id_bot,
+                                          P4 (&bot)[G], bool send, HandoffSlot<G>* out_slot,
+                                          unsigned long long* out_full, unsigned long long* out_empty,
+                                          unsigned& h_out, bool recv, float up_w10, float up_w11,
+                                          HandoffSlot<G>* in_slot, unsigned long long* in_full,
+                                          unsigned long long* in_empty, unsigned& h_in, int lane,
+                                          int c0, int C) {
+  // bottom side first: an early hand-off unblocks the warp below
+  if (send) {
+    const unsigned h = h_out++;
+    const unsigned stg = h & 1u, ph = (h >> 1) & 1u;
+    mbar_wait(out_empty + stg, ph ^ 1u);
+    const u64 w10 = pk2(s.w10, s.w10), w11 = pk2(s.w11, s.w11);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      out_slot[stg].v[0][g][lane] = p4scale(gw[g], w10);
+      out_slot[stg].v[1][g][lane] = p4scale(gw[g], w11);
+    }
+    mbar_arrive(out_full + stg);
+  } else {
+    side_q<G, FULL>(dst, gw, s.w10, s.w11, s.p10, s.p11, id_bot, bot, c0, C);
+  }
+  if (recv) {
+    const unsigned h = h_in++;
+    const unsigned stg = h & 1u, ph = (h >> 1) & 1u;
+    mbar_wait(in_full + stg, ph);
+    P4 cl[G], cr[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cl[g] = in_slot[stg].v[0][g][lane];
+      cr[g] = in_slot[stg].v[1][g][lane];
+    }
+    mbar_arrive(in_empty + stg);
+    const u64 w00 = pk2(s.w00, s.w00), w01 = pk2(s.w01, s.w01);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cl[g] = p4fma(gw[g], w00, cl[g]);
+      cr[g] = p4fma(gw[g], w01, cr[g]);
+    }
+    side_c<G, FULL>(dst, cl, cr, s.w00 != 0.f || up_w10 != 0.f, s.w01 != 0.f || up_w11 != 0.f, s.p00,
+                    s.p01, id_top, top, c0, C);
+  } else {
+    side_q<G, FULL>(dst, gw, s.w00, s.w01, s.p00, s.p01, id_top, top, c0, C);
+  }
+}
+
+template <int KMAX, int G>
+struct HandoffCtx {                  // per-pixel hand-off decisions + the CTA's slots and barriers
+  bool send[KMAX], recv[KMAX];
+  float up_w10[KMAX], up_w11[KMAX];
+  HandoffSlot<G> (*out_slot)[2];     // [KMAX][2] of the boundary below this row
+  unsigned long long (*out_full)[2], (*out_empty)[2];
+  HandoffSlot<G> (*in_slot)[2];      // boundary above this row
+  unsigned long long (*in_full)[2], (*in_empty)[2];
+  unsigned h_out[KMAX], h_in[KMAX];
+  int lane;
+};
+
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1, bool HO = false>
 __device__ __forceinline__ void pixel_q(RunPending<KMAX, G>& pend, const WarpSample& s0,
                                         const WarpSample& s1, const TG* __restrict__ gp,
                                         const TIn* __restrict__ rp, const TIn* const (&nsrc)[KMAX],
                                         float* const (&ndst)[KMAX], uint32_t taddr, u64 inv_n2,
-                                        u64 two_inv_n2, int c0, int C) {
+                                        u64 two_inv_n2, int c0, int C,
+                                        HandoffCtx<KMAX, G>* ho = nullptr) {
   typename Raw<TG>::type graw[G];
   typename Raw<TIn>::type rraw[G];
 #pragma unroll
@@ -535,14 +651,27 @@ __device__ __forceinline__ void pixel_q(RunPending<KMAX, G>& pend, const WarpSam
     if (V1) gw1[g] = p4mul(gv, p4sub(w1[g], mu));
   }
   if (V0) {
-    side_q<G, FULL>(ndst[0], gw0, s0.w00, s0.w01, s0.p00, s0.p01, pend.id_top[0], pend.top[0], c0, C);
-    side_q<G, FULL>(ndst[0], gw0, s0.w10, s0.w11, s0.p10, s0.p11, pend.id_bot[0], pend.bot[0], c0, C);
+    if (HO) {
+      scatter_h<G, FULL>(ndst[0], gw0, s0, pend.id_top[0], pend.top[0], pend.id_bot[0], pend.bot[0],
+                         ho->send[0], ho->out_slot[0], ho->out_full[0], ho->out_empty[0], ho->h_out[0],
+                         ho->recv[0], ho->up_w10[0], ho->up_w11[0], ho->in_slot[0], ho->in_full[0],
+                         ho->in_empty[0], ho->h_in[0], ho->lane, c0, C);
+    } else {
+      side_q<G, FULL>(ndst[0], gw0, s0.w00, s0.w01, s0.p00, s0.p01, pend.id_top[0], pend.top[0], c0, C);
+      side_q<G, FULL>(ndst[0], gw0, s0.w10, s0.w11, s0.p10, s0.p11, pend.id_bot[0], pend.bot[0], c0, C);
+    }
   }
   if (V1) {
-    side_q<G, FULL>(ndst[KMAX - 1], gw1, s1.w00, s1.w01, s1.p00, s1.p01, pend.id_top[KMAX - 1],
-                    pend.top[KMAX - 1], c0, C);
-    side_q<G, FULL>(ndst[KMAX - 1], gw1, s1.w10, s1.w11, s1.p10, s1.p11, pend.id_bot[KMAX - 1],
-                    pend.bot[KMAX - 1], c0, C);
+    constexpr int J = KMAX - 1;
+    if (HO) {
+      scatter_h<G, FULL>(ndst[J], gw1, s1, pend.id_top[J], pend.top[J], pend.id_bot[J], pend.bot[J],
+                         ho->send[J], ho->out_slot[J], ho->out_full[J], ho->out_empty[J], ho->h_out[J],
+                         ho->recv[J], ho->up_w10[J], ho->up_w11[J], ho->in_slot[J], ho->in_full[J],
+                         ho->in_empty[J], ho->h_in[J], ho->lane, c0, C);
+    } else {
+      side_q<G, FULL>(ndst[J], gw1, s1.w00, s1.w01, s1.p00, s1.p01, pend.id_top[J], pend.top[J], c0, C);
+      side_q<G, FULL>(ndst[J], gw1, s1.w10, s1.w11, s1.p10, s1.p11, pend.id_bot[J], pend.bot[J], c0, C);
+    }
   }
 }
 
@@ -665,109 +794,6 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 // arrivals each), and warp r+1 adds them to its own top contribution before its
 // merge-or-flush step.  Replay (tools/red_merge_sim.py): 3.5 -> 2.7 GB of RED payload.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" :: "r"(smem_u32(b)), "r"(parity) : "memory");
-}
-
-// side_q for pre-weighted contributions (left / right vectors), used by the receiving
-// side of a hand-off.
-template <int G, bool FULL>
-__device__ __forceinline__ void side_c(float* dst, const P4 (&cl)[G], const P4 (&cr)[G], bool nz_left,
-                                       bool nz_right, unsigned p_left, unsigned p_right,
-                                       unsigned& open_id, P4 (&open)[G], int c0, int C) {
-  P4 a[G];
-  if (open_id == p_left) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) a[g] = p4add(cl[g], open[g]);
-    red_group_p<G, FULL>(dst, p_left, a, c0, C);
-#pragma unroll
-    for (int g = 0; g < G; ++g) open[g] = cr[g];
-    open_id = nz_right ? p_right : kNoTap;
-  } else if (open_id == p_right && nz_right) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) open[g] = p4add(cr[g], open[g]);
-    if (nz_left) red_group_p<G, FULL>(dst, p_left, cl, c0, C);
-  } else {
-    if (open_id != kNoTap) red_group_p<G, FULL>(dst, open_id, open, c0, C);
-    if (nz_left) red_group_p<G, FULL>(dst, p_left, cl, c0, C);
-#pragma unroll
-    for (int g = 0; g < G; ++g) open[g] = cr[g];
-    open_id = nz_right ? p_right : kNoTap;
-  }
-}
-
-template <int G>
-struct HandoffSlot {                 // one stage: left and right weighted vectors, lane-private columns
-  P4 v[2][G][32];
-};
-
-// One neighbour's scatter with the hand-off protocol.  send: give the bottom side to the
-// row below; recv: take the row above's bottom side into this row's top side.
-template <int G, bool FULL>
-__device__ __forceinline__ void scatter_h(float* dst, const P4 (&gw)[G], const WarpSample& s,
-                                          unsigned& id_top, P4 (&top)[G], unsigned& id_bot,
-                                          P4 (&bot)[G], bool send, HandoffSlot<G>* out_slot,
-                                          unsigned long long* out_full, unsigned long long* out_empty,
-                                          unsigned& h_out, bool recv, float up_w10, float up_w11,
-                                          HandoffSlot<G>* in_slot, unsigned long long* in_full,
-                                          unsigned long long* in_empty, unsigned& h_in, int lane,
-                                          int c0, int C) {
-  // bottom side first: an early hand-off unblocks the warp below
-  if (send) {
-    const unsigned h = h_out++;
-    const unsigned stg = h & 1u, ph = (h >> 1) & 1u;
-    mbar_wait(out_empty + stg, ph ^ 1u);
-    const u64 w10 = pk2(s.w10, s.w10), w11 = pk2(s.w11, s.w11);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      out_slot[stg].v[0][g][lane] = p4scale(gw[g], w10);
-      out_slot[stg].v[1][g][lane] = p4scale(gw[g], w11);
-    }
-    mbar_arrive(out_full + stg);
-  } else {
-    side_q<G, FULL>(dst, gw, s.w10, s.w11, s.p10, s.p11, id_bot, bot, c0, C);
-  }
-  if (recv) {
-    const unsigned h = h_in++;
-    const unsigned stg = h & 1u, ph = (h >> 1) & 1u;
-    mbar_wait(in_full + stg, ph);
-    P4 cl[G], cr[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      cl[g] = in_slot[stg].v[0][g][lane];
-      cr[g] = in_slot[stg].v[1][g][lane];
-    }
-    mbar_arrive(in_empty + stg);
-    const u64 w00 = pk2(s.w00, s.w00), w01 = pk2(s.w01, s.w01);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      cl[g] = p4fma(gw[g], w00, cl[g]);
-      cr[g] = p4fma(gw[g], w01, cr[g]);
-    }
-    side_c<G, FULL>(dst, cl, cr, s.w00 != 0.f || up_w10 != 0.f, s.w01 != 0.f || up_w11 != 0.f, s.p00,
-                    s.p01, id_top, top, c0, C);
-  } else {
-    side_q<G, FULL>(dst, gw, s.w00, s.w01, s.p00, s.p01, id_top, top, c0, C);
-  }
-}
-
 // requires p.k == KMAX
 template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB>
 __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const SweepParams p) {
@@ -827,9 +853,12 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const
   constexpr int ppf = 32 / spp > 0 ? 32 / spp : 1;
   const int wdn = min(warp + 1, kRunRows - 1), wup = max(warp - 1, 0);
   const int bo = min(warp, kRunRows - 2), bi = max(warp - 1, 0);     // boundary below / above this row
-  unsigned h_out[KMAX], h_in[KMAX];
+  HandoffCtx<KMAX, G> ho;
+  ho.out_slot = s_slot[bo]; ho.out_full = s_full[bo]; ho.out_empty = s_empty[bo];
+  ho.in_slot = s_slot[bi]; ho.in_full = s_full[bi]; ho.in_empty = s_empty[bi];
+  ho.lane = lane;
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) h_out[j] = h_in[j] = 0u;
+  for (int j = 0; j < KMAX; ++j) ho.h_out[j] = ho.h_in[j] = 0u;
 
   if (active) {
 #pragma unroll
@@ -866,75 +895,40 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const
       const WarpSample* tab_up = s_tab[wup] + toff;
 #pragma unroll 1
       for (int i = 0; i < c.npix; ++i) {
-        WarpSample sm[KMAX];
-        bool val[KMAX], send[KMAX], recv[KMAX];
-        float uw10[KMAX], uw11[KMAX];
-        bool any = false;
+        const WarpSample s0 = tab[i * KMAX];
+        const WarpSample s1 = tab[i * KMAX + (KMAX - 1)];
+        const bool v0 = s0.p00 != kNoSample;
+        const bool v1 = KMAX == 2 && s1.p00 != kNoSample;
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
-          sm[j] = tab[i * KMAX + j];
-          val[j] = sm[j].p00 != kNoSample;
-          any |= val[j];
-          send[j] = recv[j] = false;
-          uw10[j] = uw11[j] = 0.f;
-          if (val[j]) {
+          const WarpSample& sj = j == 0 ? s0 : s1;
+          const bool vj = j == 0 ? v0 : v1;
+          ho.send[j] = ho.recv[j] = false;
+          ho.up_w10[j] = ho.up_w11[j] = 0.f;
+          if (vj) {
             if (warp + 1 < kRunRows) {
               const WarpSample& dn = tab_dn[i * KMAX + j];
-              send[j] = dn.p00 != kNoSample && dn.p00 == sm[j].p10 && dn.p01 == sm[j].p11;
+              ho.send[j] = dn.p00 != kNoSample && dn.p00 == sj.p10 && dn.p01 == sj.p11;
             }
             if (warp > 0) {
               const WarpSample& up = tab_up[i * KMAX + j];
-              recv[j] = up.p00 != kNoSample && up.p10 == sm[j].p00 && up.p11 == sm[j].p01;
-              uw10[j] = up.w10;
-              uw11[j] = up.w11;
+              ho.recv[j] = up.p00 != kNoSample && up.p10 == sj.p00 && up.p11 == sj.p01;
+              ho.up_w10[j] = up.w10;
+              ho.up_w11[j] = up.w11;
             }
           }
         }
         const TG* gp = g_d + i * C;
         const TIn* rp = ref_row + i * C;
-        typename Raw<TG>::type graw[G];
-        typename Raw<TIn>::type rraw[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const bool on = group_on<FULL>(c.c0, g, C);
-          graw[g] = on ? Raw<TG>::ld_stream_na(gp + 128 * g) : Raw<TG>::zero();
-          rraw[g] = on ? Raw<TIn>::ld(rp + 128 * g) : Raw<TIn>::zero();
-        }
-        RawTaps<TIn, G> traw[KMAX];
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j)
-          if (val[j]) load_taps<TIn, G, FULL>(nsrc[j], sm[j], c.c0, C, traw[j]);
-        P4 wv[KMAX][G], gw[KMAX][G];
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-          if (val[j]) {
-            blend_taps<TIn, G>(traw[j], sm[j], wv[j]);
-          } else {
-#pragma unroll
-            for (int g = 0; g < G; ++g) wv[j][g] = p4zero();
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const P4 ref = p4from(rraw[g]);
-          P4 mu = ref;
-#pragma unroll
-          for (int j = 0; j < KMAX; ++j) mu = p4add(mu, wv[j][g]);
-          mu = p4scale(mu, inv_n2);
-          const P4 gv = p4scale(p4from(graw[g]), two_inv_n2);
-          const uint32_t ta = tbase + 4u * (uint32_t)(i * G + g);
-          tmem_st4(ta, p4fma(gv, p4sub(ref, mu), tmem_ld4(ta)));
-#pragma unroll
-          for (int j = 0; j < KMAX; ++j) gw[j][g] = p4mul(gv, p4sub(wv[j][g], mu));
-        }
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-          if (!val[j]) continue;
-          scatter_h<G, FULL>(ndst[j], gw[j], sm[j], pend.id_top[j], pend.top[j], pend.id_bot[j],
-                             pend.bot[j], send[j], s_slot[bo][j], s_full[bo][j], s_empty[bo][j],
-                             h_out[j], recv[j], uw10[j], uw11[j], s_slot[bi][j], s_full[bi][j],
-                             s_empty[bi][j], h_in[j], lane, c.c0, C);
-        }
+        const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
+        if (v0 && v1)
+          pixel_q<TIn, TG, KMAX, G, FULL, true, true, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+        else if (v0)
+          pixel_q<TIn, TG, KMAX, G, FULL, true, false, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+        else if (v1)
+          pixel_q<TIn, TG, KMAX, G, FULL, false, true, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+        else
+          pixel_q<TIn, TG, KMAX, G, FULL, false, false, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
       }
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
