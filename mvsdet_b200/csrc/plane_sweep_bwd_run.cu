@@ -16,6 +16,9 @@ namespace mvsd {
 #ifndef MVSD_KRUN
 #define MVSD_KRUN 8
 #endif
+#ifndef MVSD_RUNQ_MINB
+#define MVSD_RUNQ_MINB 3         // CTAs per SM the lean kernel is compiled for (168 registers)
+#endif
 constexpr int kRun = MVSD_KRUN;            // pixels per warp run
 constexpr int kRunRows = 4;                // rows (= warps) per CTA
 constexpr int kRunThreads = kRunRows * 32;
@@ -974,7 +977,7 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
 #define MVSD_RUN(KM, GG, FU)                                                              \
   do {                                                                                    \
     if (tuning(5) == 8) sweep_bwd_runh_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
-    else if (lean) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (lean) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, false><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4, false><<<grid, kRunThreads, 0, st>>>(p); \
