@@ -195,6 +195,19 @@ int mvsd_prob_norm_bwd(const float* prob, const float* g_pn, float* g_prob,
 int mvsd_voxel_normalize(const float* sum, const int32_t* count, float* out,
                          int layout, int C, int N, void* stream);
 
+/* View-sharded scene (reference views split over `world` GPUs of one NVLink domain):
+ * the sum over views of mvsdet.py:511-515 / :681-682 across ranks, fused with the
+ * normalisation, over peer memory instead of an all-reduce.  part_ptrs / out_ptrs are
+ * DEVICE arrays of `world` peer pointers (e.g. torch symmetric memory
+ * buffer_ptrs_dev): each peer buffer is [C*N] fp32 (partial sums in `layout`) followed
+ * by [N] int32 (partial valid counts); the result buffers get [C*N] fp32 volume_mean
+ * followed by [N] int32 counts, identical bits on every rank.  The caller puts a
+ * cross-rank barrier before (all partials written) and after (all results delivered)
+ * this call.  count_local: [N] int32 scratch on this rank.                         */
+int mvsd_voxel_reduce_p2p(const void* const* part_ptrs, void* const* out_ptrs,
+                          int32_t* count_local, int world, int rank, int layout, int C, int N,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

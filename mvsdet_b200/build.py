@@ -24,7 +24,7 @@ LIB = os.path.join(LIBDIR, "libmvsdet_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
 SOURCES = ("capi.cu", "pack.cu", "plane_sweep_fwd.cu", "plane_sweep_bwd.cu", "plane_sweep_bwd_run.cu", "plane_sweep_bwd_blk.cu", "plane_sweep_bwd_rows.cu",
            "depth_topk.cu",
-           "backproject.cu")
+           "backproject.cu", "voxel_p2p.cu")
 HEADERS = (os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "plane_sweep.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "mvsdet_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -297,17 +297,22 @@ def _zeros_strided_like(t: torch.Tensor) -> torch.Tensor:
 
 class _BackprojectAggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, points, projection, est_depth, est_dens, vs_z, h, w, mode, channels_first):
+    def forward(ctx, feat, points, projection, est_depth, est_dens, vs_z, h, w, mode, channels_first,
+                out=None, count=None):
         v, c, fh, fw = feat.shape
         t = est_depth.shape[1]
         n = points.numel() // 3
         dev = feat.device
         sv, st, sy, sx = est_depth.stride()
-        if channels_first:
-            out = torch.empty((c, n), dtype=torch.float32, device=dev)
-        else:
-            out = torch.empty((n, c), dtype=torch.float32, device=dev)
-        count = torch.empty((n,), dtype=torch.int32, device=dev)
+        shape = (c, n) if channels_first else (n, c)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous fp32 {shape} tensor (memory order of the volume)")
+        if count is None:
+            count = torch.empty((n,), dtype=torch.int32, device=dev)
+        elif count.numel() != n or count.dtype != torch.int32 or not count.is_contiguous():
+            raise ValueError("count must be a contiguous int32 [N] tensor")
         _lib.call("mvsd_backproject_fwd", feat.data_ptr(), _code(feat.dtype), fh, fw,
                   points.data_ptr(), projection.data_ptr(), est_depth.data_ptr(),
                   est_dens.data_ptr(), sv, sy, sx, st, float(vs_z), mode, out.data_ptr(),
@@ -341,7 +346,7 @@ class _BackprojectAggregate(torch.autograd.Function):
         _lib.call("mvsd_prob_norm_bwd", est_dens.data_ptr(), g_pn.data_ptr(), g_prob.data_ptr(),
                   sv, sy, sx, st, v, h, w, t, _stream())
         g_feat = g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)
-        return g_feat, None, None, None, g_prob, None, None, None, None, None
+        return g_feat, None, None, None, g_prob, None, None, None, None, None, None, None
 
 
 def _check_hyp(name, t, v, fh, fw):
@@ -354,7 +359,8 @@ def _check_hyp(name, t, v, fh, fw):
 
 def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: float,
                           height: int, width: int, *, mode: str = "mean",
-                          channels_first: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                          channels_first: bool = True, out: Optional[torch.Tensor] = None,
+                          count_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused backproject_Weigh (mvsdet.py:1372-1492) + aggregation (:511-515,
     :681-682).
 
@@ -364,7 +370,9 @@ def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: f
     mode        "mean" -> (volume_mean [C,N], count [N] int32)
                 "sum"  -> (volume_sum  [C,N], count) partials for multi-GPU
     The result is logical [C,N]; with channels_first=False its memory is [N,C]
-    (channels_last_3d once viewed as [C,nx,ny,nz])."""
+    (channels_last_3d once viewed as [C,nx,ny,nz]).  ``out`` / ``count_out``: write into
+    caller-owned buffers (memory order of the volume: [C,N] or [N,C] contiguous) -- the
+    view-sharded path lets the kernel write its partials straight into peer-mapped memory."""
     _need_cuda("feat", feat)
     if not _is_nhwc(feat):
         raise ValueError("feat must be channels_last; use ops.pack_features")
@@ -382,7 +390,8 @@ def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: f
     m = {"mean": BP_MEAN, "sum": BP_SUM}[mode]
     return _BackprojectAggregate.apply(feat, points.contiguous().float(),
                                        projection.contiguous().float(), est_depth, est_dens,
-                                       float(vs_z), int(height), int(width), m, bool(channels_first))
+                                       float(vs_z), int(height), int(width), m, bool(channels_first),
+                                       out, count_out)
 
 
 class _BackprojectPerView(torch.autograd.Function):

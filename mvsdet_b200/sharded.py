@@ -30,6 +30,8 @@ from typing import Callable, Dict, List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from ._lib import CHANNELS_FIRST, CHANNELS_LAST
+
 __all__ = ["partition_views", "halo_views", "pack_partials", "unpack_partials",
            "allreduce_partials", "LocalGeometry", "ShardedSceneForward"]
 
@@ -102,6 +104,58 @@ def allreduce_partials(buf: torch.Tensor, group=None) -> torch.Tensor:
     return buf
 
 
+class P2PVoxelReducer:
+    """Sum-over-ranks + normalise of the voxel partials over NVLink peer memory
+    (``mvsd_voxel_reduce_p2p``): one reduce-scatter / normalise / all-gather kernel
+    bracketed by two cross-rank barriers, instead of an NCCL all-reduce followed by a
+    normalise kernel.  Buffers are torch symmetric memory (P2P-mapped on every rank of
+    the group); torch provides the allocation, the pointer exchange and the barrier
+    kernel, the data path is ours.
+
+        red = P2PVoxelReducer(C, N, channels_first, device, group)
+        volume_mean, count = red(volume_sum, count)        # identical bits on every rank
+    """
+
+    def __init__(self, channels: int, n_voxels: int, channels_first: bool, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("P2PVoxelReducer needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.c, self.n, self.cfirst = int(channels), int(n_voxels), bool(channels_first)
+        self.total = self.c * self.n
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.part = symm.empty(self.total + self.n, dtype=torch.float32, device=device)
+        self.out = symm.empty(self.total + self.n, dtype=torch.float32, device=device)
+        self.h_part = symm.rendezvous(self.part, self.group)
+        self.h_out = symm.rendezvous(self.out, self.group)
+        self.count_local = torch.empty(self.n, dtype=torch.int32, device=device)
+
+    def partial_buffers(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(sum, count) views of this rank's peer-mapped partial buffer, in the volume's
+        memory order: pass them as ``out=`` / ``count_out=`` of the back-projection so the
+        kernel writes its partials where the peers will read them."""
+        shape = (self.c, self.n) if self.cfirst else (self.n, self.c)
+        return self.part[:self.total].view(shape), self.part[self.total:].view(torch.int32)
+
+    def __call__(self, volume_sum: torch.Tensor, count: torch.Tensor):
+        from . import _lib
+        mem = volume_sum if volume_sum.is_contiguous() else volume_sum.t()
+        if not mem.is_contiguous() or mem.numel() != self.total:
+            raise ValueError("volume_sum must be [C,N] contiguous or the transpose of a contiguous [N,C]")
+        if mem.data_ptr() != self.part.data_ptr():           # not already written in place
+            self.part[:self.total].copy_(mem.reshape(-1))
+            self.part[self.total:].view(torch.int32).copy_(count.reshape(-1))
+        self.h_part.barrier(channel=0)          # every rank's partials are complete and visible
+        _lib.call("mvsd_voxel_reduce_p2p", self.h_part.buffer_ptrs_dev, self.h_out.buffer_ptrs_dev,
+                  self.count_local.data_ptr(), self.world, self.rank,
+                  CHANNELS_FIRST if self.cfirst else CHANNELS_LAST, self.c, self.n,
+                  torch.cuda.current_stream().cuda_stream)
+        self.h_out.barrier(channel=0)           # every rank's slice has landed in every out buffer
+        vol = self.out[:self.total]
+        vol = vol.view(self.c, self.n) if self.cfirst else vol.view(self.n, self.c).t()
+        return vol, self.out[self.total:].view(torch.int32)
+
+
 class ShardedSceneForward:
     """Forward of one scene with the reference views split over the group.
 
@@ -114,9 +168,11 @@ class ShardedSceneForward:
     to overlap it with inside one scene; a multi-scene caller overlaps it with
     the next scene's sweep by calling from a side stream)."""
 
-    def __init__(self, hot_path, group=None):
+    def __init__(self, hot_path, group=None, p2p: bool = False):
         self.hot = hot_path
         self.group = group
+        self.p2p = p2p                 # combine over NVLink peer memory instead of NCCL all-reduce
+        self._reducer = None
 
     def _world(self) -> Tuple[int, int]:
         if dist.is_available() and dist.is_initialized():
@@ -158,7 +214,8 @@ class ShardedSceneForward:
         return out.permute(0, 3, 1, 2)
 
     def local_partials(self, feature: torch.Tensor, img_meta: dict, cost_net: Callable,
-                       geometry: Optional[LocalGeometry] = None, rank_world: Optional[Tuple[int, int]] = None):
+                       geometry: Optional[LocalGeometry] = None, rank_world: Optional[Tuple[int, int]] = None,
+                       partial_out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         """This rank's contribution before the collective: (volume_sum logical
         [C,N], count int32 [N], (begin, end)).  ``rank_world`` overrides the
         process group (used by the single-GPU tests to play every rank)."""
@@ -187,7 +244,9 @@ class ShardedSceneForward:
             vol_sum, count = ops.backproject_aggregate(
                 feat_cl[:end - begin], geo.points, geo.projection, est_depth, est_dens,
                 hot.voxel_size[2], geo.height, geo.width, mode="sum",
-                channels_first=hot.channels_first_volume)
+                channels_first=hot.channels_first_volume,
+                out=None if partial_out is None else partial_out[0],
+                count_out=None if partial_out is None else partial_out[1])
         else:                                   # more ranks than views: contribute zeros
             shape = (c, n) if hot.channels_first_volume else (n, c)
             vol_sum = torch.zeros(shape, dtype=torch.float32, device=dev)
@@ -205,11 +264,19 @@ class ShardedSceneForward:
         c = feature.shape[1]
         nx, ny, nz = hot.n_voxels
         n = nx * ny * nz
-        vol_sum, count, (begin, end) = self.local_partials(feature, img_meta, cost_net, geometry)
-        buf = pack_partials(vol_sum.detach(), count)
-        allreduce_partials(buf, self.group)
-        vol_sum, count = unpack_partials(buf, c, n, hot.channels_first_volume)
-        volume_mean = ops.voxel_normalize(vol_sum, count)
+        use_p2p = self.p2p and self._world()[1] > 1
+        if use_p2p and self._reducer is None:
+            self._reducer = P2PVoxelReducer(c, n, hot.channels_first_volume, feature.device, self.group)
+        vol_sum, count, (begin, end) = self.local_partials(
+            feature, img_meta, cost_net, geometry,
+            partial_out=self._reducer.partial_buffers() if use_p2p else None)
+        if use_p2p:
+            volume_mean, count = self._reducer(vol_sum.detach(), count)
+        else:
+            buf = pack_partials(vol_sum.detach(), count)
+            allreduce_partials(buf, self.group)
+            vol_sum, count = unpack_partials(buf, c, n, hot.channels_first_volume)
+            volume_mean = ops.voxel_normalize(vol_sum, count)
         vm = (volume_mean.view(c, nx, ny, nz) if volume_mean.is_contiguous()
               else volume_mean.unflatten(1, (nx, ny, nz)))
         return dict(volume_mean=vm, valid=count.view(1, nx, ny, nz).float(), count=count,

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--views", type=int, default=80)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--feature-dtype", default="bf16")
+    ap.add_argument("--p2p", action="store_true",
+                    help="also time the combine over NVLink peer memory (mvsd_voxel_reduce_p2p) instead of NCCL")
     ap.add_argument("--graph", action="store_true", help="also time a CUDA-graph replay of the sharded forward (measured: 0.845 vs 0.873 ms eager at "
                          "V=80, N=2 -- the launch gaps are not what limits the sharded path)")
     a = ap.parse_args()
@@ -79,6 +81,21 @@ def main():
            "scenes_per_s_sharded": round(1e3 / ms_sh, 2), "feature_dtype": a.feature_dtype,
            "allreduce_bytes": int(out_sh["volume_mean"].numel() * 4 + out_sh["count"].numel() * 4),
            "neighbour_features": "fp32 FPN maps of all views resident on every rank; each rank packs its block + halo views only"}
+    if a.p2p and world > 1:
+        runner_p2p = sharded.ShardedSceneForward(hot, p2p=True)
+
+        def sharded_p2p():
+            return runner_p2p(feat, scene["img_meta"], cost_regularization=lambda var: cost[begin:end],
+                              geometry=geo_local)
+
+        ms_p, out_p = timed(sharded_p2p)
+        res.update(ms_sharded_forward_p2p=round(ms_p, 4),
+                   p2p_matches_nccl_count=bool(torch.equal(out_p["count"], out_sh["count"])),
+                   p2p_max_abs_diff_vs_nccl=float((out_p["volume_mean"] - out_sh["volume_mean"]).abs().max()))
+        chk = out_p["volume_mean"].double().sum().reshape(1)
+        gathered = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        res["p2p_replicas_identical"] = all(float(g) == float(gathered[0]) for g in gathered)
     # the same forward captured once into a CUDA graph (kernels + the NCCL all-reduce) and
     # replayed: removes the eager launch gaps, which are comparable to the per-rank GPU work
     if a.graph:
