@@ -321,7 +321,16 @@ def run_own_arm(args, cfg, cfg_json):
     if os.path.isfile(ncu_traffic):
         try:
             with open(ncu_traffic) as fh:
-                roofline["traffic"] = json.load(fh).get(top)
+                tj = json.load(fh)
+            roofline["traffic"] = tj.get(top)
+            red = tj.get(top + "_red_payload")
+            if red:
+                # what actually limits the scatter kernel: fp32 REDs into L2.  Ceiling measured by
+                # tools/microbench_red.cu on this pool's B200 (profiles/r01_b_microbench_red.txt).
+                red_gbs = red / (kernels[top]["ms"] * 1e-3) / 1e9
+                roofline["limiter"] = {"what": "fp32 red.global.add.v4 payload into L2 (ncu l1tex2xbar write bytes)",
+                                       "red_payload_bytes": red, "achieved_gbs": round(red_gbs, 1),
+                                       "ceiling_gbs": 5700.0, "frac": round(red_gbs / 5700.0, 3)}
         except Exception:
             pass
 

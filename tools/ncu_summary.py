@@ -65,6 +65,21 @@ def traffic(paths, out_path):
                     acc.setdefault(key, []).append(to_bytes(r[ri], units[ri]) + to_bytes(r[wi], units[wi]))
                     break
     res = {k: int(sum(v) / len(v)) for k, v in acc.items()}
+    # RED payload of the plane-sweep backward (bytes leaving the SMs towards L2: the gradient
+    # scatter; the kernel has no other global writes) -- bench.py reports it next to the
+    # measured fp32-RED ceiling
+    red = []
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units = rows[0], rows[1]
+        if "l1tex__m_l1tex2xbar_write_bytes.sum" not in hdr:
+            continue
+        ki, wi = hdr.index("Kernel Name"), hdr.index("l1tex__m_l1tex2xbar_write_bytes.sum")
+        red += [to_bytes(r[wi], units[wi]) for r in rows[2:] if "sweep_bwd" in r[ki]]
+    if red:
+        res["plane_sweep_bwd_red_payload"] = int(sum(red) / len(red))
     with open(out_path, "w") as fh:
         json.dump(res, fh, indent=1, sort_keys=True)
     print(json.dumps(res))
