@@ -5,12 +5,17 @@ Reference views are independent in the plane sweep and in the back-projection
 (per-view loops, projects/NeRF-Det/nerfdet/mvsdet.py:453, :1401, :1458); only
 the sum over views and the per-voxel valid count couple them (mvsdet.py:511-515).
 So every rank sweeps a contiguous block of reference views, back-projects them
-into *partial* voxel sums and counts (``MVSD_BP_SUM``), the partials are
-combined with ONE all-reduce of ``C*N + N`` fp32 words (26.3 MB for the shipped
-40x40x16 grid) -- NCCL over NVLink on the B200 box -- and every rank applies the
-same ``sum / (count + 1e-8)`` (mvsdet.py:514-515, :681-682), giving replicas
-that are bit-identical across ranks.  The counts travel as fp32 in the same
-buffer: they are integers <= V <= 2^24, so the sum is exact.
+into *partial* voxel sums and counts (``MVSD_BP_SUM``), and the partials
+(``C*N + N`` words, 26.3 MB for the shipped 40x40x16 grid) are combined once per
+scene, giving replicas that are bit-identical across ranks.  Two combines exist:
+
+* ``P2PVoxelReducer`` (default): the back-projection writes its partials into a
+  peer-mapped buffer and ``mvsd_voxel_reduce_p2p`` does reduce-scatter +
+  ``sum / (count + 1e-8)`` (mvsdet.py:514-515, :681-682) + all-gather in one kernel
+  over NVLink peer pointers (V=80 on 8 B200: 0.38 ms per scene against 0.59 ms);
+* ``p2p=False``: ONE NCCL all-reduce of the packed partials, then
+  ``mvsd_voxel_normalize`` on every rank.  The counts travel as fp32 in the same
+  buffer: they are integers <= V <= 2^24, so the sum is exact.
 
 The FPN feature maps of all V views are resident on every rank (the k=2 pose
 neighbours of a local view may belong to another rank, SURVEY.md 8e caveat 1);
@@ -168,10 +173,10 @@ class ShardedSceneForward:
     to overlap it with inside one scene; a multi-scene caller overlaps it with
     the next scene's sweep by calling from a side stream)."""
 
-    def __init__(self, hot_path, group=None, p2p: bool = False):
+    def __init__(self, hot_path, group=None, p2p: bool = True):
         self.hot = hot_path
         self.group = group
-        self.p2p = p2p                 # combine over NVLink peer memory instead of NCCL all-reduce
+        self.p2p = p2p                 # combine over NVLink peer memory (default); False = NCCL all-reduce
         self._reducer = None
 
     def _world(self) -> Tuple[int, int]:

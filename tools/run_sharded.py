@@ -46,7 +46,7 @@ def main():
     feat = scene["feature"].to(dev)
     cost = scene["cost_out"].to(dev)
     begin, end = sharded.partition_views(cfg.n_views, world, rank)
-    runner = sharded.ShardedSceneForward(hot)
+    runner = sharded.ShardedSceneForward(hot, p2p=False)       # NCCL all-reduce + normalise
     geo_local = runner.local_geometry(scene["img_meta"], cfg.n_views, dev)
     geo_full = hot.geometry(scene["img_meta"], dev)
 
