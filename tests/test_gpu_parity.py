@@ -256,3 +256,27 @@ def test_plane_sweep_bwd_variants(case, variant):
         _lib.set_tuning(5, old)
     _close(res["g_feature_from_variance"], gold["g_feature_from_variance"],
            f"{case}: variant {variant} g_feature_from_variance")
+
+
+@pytest.mark.parametrize("hw", [(13, 21), (9, 7), (17, 40)])
+@pytest.mark.parametrize("variant", [0, 5, 8])
+def test_ragged_feature_map_sizes(hw, variant):
+    """Feature maps whose height is not a multiple of the CTA's 4 rows and whose width is
+    not a multiple of the 8-pixel run (partial runs, idle warps, hand-off with a missing
+    row below), default backward and the two block variants: whole chain vs the oracle."""
+    from mvsdet_b200 import _lib
+    from mvsdet_b200.scene import make_scene, tiny_config
+    h, w = hw
+    cfg = tiny_config(n_views=4, channels=40, num_depth=6, img_shape=(4 * h - 1, 4 * w),
+                      pad_shape=(4 * h, 4 * w), ori_shape=(16 * h - 4, 16 * w))
+    scene = make_scene(cfg, seed=21)
+    ref = oracle_chain(scene)
+    old = _lib.set_tuning(5, variant)
+    try:
+        res = cuda_chain(scene)
+    finally:
+        _lib.set_tuning(5, old)
+    assert np.array_equal(res["count"].cpu().numpy().reshape(ref["count"].shape), ref["count"].numpy())
+    assert np.array_equal(res["est_idx"].cpu().numpy(), ref["est_idx"].numpy())
+    for key in ("variance", "volume_mean", "g_feature_from_variance", "g_feature_from_voxels"):
+        _close(res[key], ref[key], f"{hw} variant {variant}: {key}")
