@@ -24,7 +24,7 @@ from typing import Callable, Dict, Optional, Sequence
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import library, ops
 from .geometry import SceneGeometry, scene_geometry
 
 __all__ = ["MVSDetHotPath"]
@@ -36,7 +36,8 @@ class MVSDetHotPath(nn.Module):
                  cost_regularization: Optional[nn.Module] = None, stride: int = 4,
                  feature_dtype: torch.dtype = torch.float32,
                  variance_dtype: torch.dtype = torch.float32,
-                 channels_first_volume: bool = True, num_neighbors: int = 2):
+                 channels_first_volume: bool = True, num_neighbors: int = 2,
+                 dispatcher_ops: bool = False):
         super().__init__()
         self.n_voxels = [int(n) for n in n_voxels]
         self.voxel_size = [float(s) for s in voxel_size]
@@ -51,6 +52,9 @@ class MVSDetHotPath(nn.Module):
         self.variance_dtype = variance_dtype
         self.channels_first_volume = channels_first_volume
         self.num_neighbors = num_neighbors      # k = min(2, V-1), mvsdet.py:432
+        # True: go through the torch.library ops (torch.ops.mvsdet_b200.*, library.py) instead of
+        # the autograd.Function layer -- same launchers, same kernels, traceable with fake tensors
+        self.dispatcher_ops = bool(dispatcher_ops)
 
     def geometry(self, img_meta: dict, device, view_slice=None) -> SceneGeometry:
         return scene_geometry(img_meta, stride=self.stride, near_far_range=self.near_far_range,
@@ -60,13 +64,25 @@ class MVSDetHotPath(nn.Module):
 
     # -- stages ------------------------------------------------------------
     def variance(self, feat_cl: torch.Tensor, geo: SceneGeometry, ref_begin: int = 0) -> torch.Tensor:
+        if self.dispatcher_ops:
+            if self.variance_dtype not in (torch.float32, torch.bfloat16):
+                raise ValueError("variance_dtype must be float32 or bfloat16")
+            return library.plane_sweep_variance(feat_cl, geo.neighbor_ids, geo.hom, geo.depth_values,
+                                                self.variance_dtype == torch.bfloat16, ref_begin)
         return ops.plane_sweep_variance(feat_cl, geo.neighbor_ids, geo.hom, geo.depth_values,
                                         out_dtype=self.variance_dtype, ref_begin=ref_begin)
 
     def hypotheses(self, cost_out: torch.Tensor):
+        if self.dispatcher_ops:
+            return library.depth_topk(cost_out, self.near_far_range[0], self.depth_interval, self.topk)
         return ops.depth_topk(cost_out, self.near_far_range[0], self.depth_interval, self.topk)
 
     def voxels(self, feat_cl, geo: SceneGeometry, est_depth, est_dens, mode: str = "mean"):
+        if self.dispatcher_ops:
+            return library.backproject_aggregate(feat_cl, geo.points, geo.projection, est_depth, est_dens,
+                                                 self.voxel_size[2], geo.height, geo.width,
+                                                 {"mean": False, "sum": True}[mode],
+                                                 self.channels_first_volume)
         return ops.backproject_aggregate(feat_cl, geo.points, geo.projection, est_depth, est_dens,
                                          self.voxel_size[2], geo.height, geo.width, mode=mode,
                                          channels_first=self.channels_first_volume)

@@ -117,17 +117,39 @@ def pack_features(x: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.
 # --------------------------------------------------------------------------
 # plane sweep
 # --------------------------------------------------------------------------
+def _sweep_fwd_raw(feat, nbr_ids, hom, depth_values, out_dtype, ref_begin):
+    """enqueue mvsd_plane_sweep_fwd; -> variance, logical [V,C,D,H,W] in channels_last_3d"""
+    _, c, h, w = feat.shape
+    v = nbr_ids.shape[0]
+    d = depth_values.shape[1]
+    k = nbr_ids.shape[1]
+    out = _empty_ndhwc(v, c, d, h, w, out_dtype, feat.device)
+    _lib.call("mvsd_plane_sweep_fwd", feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids),
+              _ptr(hom), depth_values.data_ptr(), out.data_ptr(), _code(out_dtype),
+              CHANNELS_LAST, v, c, d, h, w, k, ref_begin, _stream())
+    return out
+
+
+def _sweep_bwd_raw(g, feat, nbr_ids, hom, depth_values, ref_begin):
+    """enqueue mvsd_plane_sweep_bwd; -> dL/dfeat in feat's dtype, channels_last"""
+    vf, c, h, w = feat.shape
+    v = nbr_ids.shape[0]
+    d = depth_values.shape[1]
+    k = nbr_ids.shape[1]
+    gdt = torch.bfloat16 if (g.dtype == torch.bfloat16 and feat.dtype == torch.bfloat16) else torch.float32
+    g = _as_ndhwc(g, gdt)
+    g_feat = _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
+    _lib.call("mvsd_plane_sweep_bwd", g.data_ptr(), _code(g.dtype), CHANNELS_LAST,
+              feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids), _ptr(hom),
+              depth_values.data_ptr(), g_feat.data_ptr(), v, c, d, h, w, k, ref_begin,
+              _stream())
+    return g_feat.to(feat.dtype) if feat.dtype != torch.float32 else g_feat
+
+
 class _PlaneSweepVariance(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, nbr_ids, hom, depth_values, out_dtype, ref_begin):
-        _, c, h, w = feat.shape
-        v = nbr_ids.shape[0]
-        d = depth_values.shape[1]
-        k = nbr_ids.shape[1]
-        out = _empty_ndhwc(v, c, d, h, w, out_dtype, feat.device)
-        _lib.call("mvsd_plane_sweep_fwd", feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids),
-                  _ptr(hom), depth_values.data_ptr(), out.data_ptr(), _code(out_dtype),
-                  CHANNELS_LAST, v, c, d, h, w, k, ref_begin, _stream())
+        out = _sweep_fwd_raw(feat, nbr_ids, hom, depth_values, out_dtype, ref_begin)
         ctx.save_for_backward(feat, nbr_ids, hom, depth_values)
         ctx.ref_begin = ref_begin
         return out
@@ -135,18 +157,7 @@ class _PlaneSweepVariance(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         feat, nbr_ids, hom, depth_values = ctx.saved_tensors
-        vf, c, h, w = feat.shape
-        v = nbr_ids.shape[0]
-        d = depth_values.shape[1]
-        k = nbr_ids.shape[1]
-        gdt = torch.bfloat16 if (g.dtype == torch.bfloat16 and feat.dtype == torch.bfloat16) else torch.float32
-        g = _as_ndhwc(g, gdt)
-        g_feat = _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
-        _lib.call("mvsd_plane_sweep_bwd", g.data_ptr(), _code(g.dtype), CHANNELS_LAST,
-                  feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids), _ptr(hom),
-                  depth_values.data_ptr(), g_feat.data_ptr(), v, c, d, h, w, k, ctx.ref_begin,
-                  _stream())
-        g_feat = g_feat.to(feat.dtype) if feat.dtype != torch.float32 else g_feat
+        g_feat = _sweep_bwd_raw(g, feat, nbr_ids, hom, depth_values, ctx.ref_begin)
         return g_feat, None, None, None, None, None
 
 
@@ -227,41 +238,55 @@ def _cost_strides(cost_out: torch.Tensor):
     return cost_out, sv, sc, sd, sw
 
 
+def _topk_fwd_raw(cost_out, near, interval, topk, raw):
+    """enqueue mvsd_depth_topk_fwd; -> (cost_out as the kernel read it, the six outputs)"""
+    cost_out, sv, sc, sd, sp = _cost_strides(cost_out)
+    v, _, d, h, w = cost_out.shape
+    dev = cost_out.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    prob = torch.empty((v, d, h, w), **f32)
+    off = torch.empty((v, d, h, w), **f32)
+    est_depth = torch.empty((v, topk, h, w), **f32)
+    est_dens = torch.empty((v, topk, h, w), **f32)
+    est_idx = torch.empty((v, topk, h, w), dtype=torch.int64, device=dev)
+    coding = torch.empty((v, h, w), **f32)
+    _lib.call("mvsd_depth_topk_fwd", cost_out.data_ptr(), sv, sc, sd, sp, prob.data_ptr(),
+              off.data_ptr(), est_depth.data_ptr(), est_dens.data_ptr(), est_idx.data_ptr(),
+              coding.data_ptr(), float(near), float(interval), int(raw), v, d, h, w, topk, _stream())
+    return cost_out, (prob, off, est_depth, est_dens, est_idx, coding)
+
+
+def _topk_bwd_raw(cost_out, est_idx, g_prob, g_off, g_depth, g_dens, g_coding, near, interval,
+                  topk, raw):
+    """enqueue mvsd_depth_topk_bwd (any of the five upstream gradients may be None)"""
+    cost_out, sv, sc, sd, sp = _cost_strides(cost_out)
+    v, _, d, h, w = cost_out.shape
+
+    def prep(g):
+        return None if g is None else g.contiguous().float()
+    g_prob, g_off, g_depth, g_dens, g_coding = map(prep, (g_prob, g_off, g_depth, g_dens, g_coding))
+    g_cost = torch.empty((v, 2, d, h, w), dtype=torch.float32, device=cost_out.device)
+    _lib.call("mvsd_depth_topk_bwd", cost_out.data_ptr(), sv, sc, sd, sp, est_idx.data_ptr(),
+              _ptr(g_prob), _ptr(g_off), _ptr(g_depth), _ptr(g_dens), _ptr(g_coding),
+              g_cost.data_ptr(), float(near), float(interval), int(raw), v, d, h, w, topk, _stream())
+    return g_cost
+
+
 class _DepthTopk(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cost_out, near, interval, topk, raw):
-        cost_out, sv, sc, sd, sp = _cost_strides(cost_out)
-        v, _, d, h, w = cost_out.shape
-        dev = cost_out.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        prob = torch.empty((v, d, h, w), **f32)
-        off = torch.empty((v, d, h, w), **f32)
-        est_depth = torch.empty((v, topk, h, w), **f32)
-        est_dens = torch.empty((v, topk, h, w), **f32)
-        est_idx = torch.empty((v, topk, h, w), dtype=torch.int64, device=dev)
-        coding = torch.empty((v, h, w), **f32)
-        _lib.call("mvsd_depth_topk_fwd", cost_out.data_ptr(), sv, sc, sd, sp, prob.data_ptr(),
-                  off.data_ptr(), est_depth.data_ptr(), est_dens.data_ptr(), est_idx.data_ptr(),
-                  coding.data_ptr(), float(near), float(interval), int(raw), v, d, h, w, topk, _stream())
-        ctx.save_for_backward(cost_out, est_idx)
+        cost_out, outs = _topk_fwd_raw(cost_out, near, interval, topk, raw)
+        ctx.save_for_backward(cost_out, outs[4])
         ctx.consts = (float(near), float(interval), topk, int(raw))
-        ctx.mark_non_differentiable(est_idx)
-        return prob, off, est_depth, est_dens, est_idx, coding
+        ctx.mark_non_differentiable(outs[4])
+        return outs
 
     @staticmethod
     def backward(ctx, g_prob, g_off, g_depth, g_dens, _g_idx, g_coding):
         cost_out, est_idx = ctx.saved_tensors
         near, interval, topk, raw = ctx.consts
-        cost_out, sv, sc, sd, sp = _cost_strides(cost_out)
-        v, _, d, h, w = cost_out.shape
-
-        def prep(g):
-            return None if g is None else g.contiguous().float()
-        g_prob, g_off, g_depth, g_dens, g_coding = map(prep, (g_prob, g_off, g_depth, g_dens, g_coding))
-        g_cost = torch.empty((v, 2, d, h, w), dtype=torch.float32, device=cost_out.device)
-        _lib.call("mvsd_depth_topk_bwd", cost_out.data_ptr(), sv, sc, sd, sp, est_idx.data_ptr(),
-                  _ptr(g_prob), _ptr(g_off), _ptr(g_depth), _ptr(g_dens), _ptr(g_coding),
-                  g_cost.data_ptr(), near, interval, raw, v, d, h, w, topk, _stream())
+        g_cost = _topk_bwd_raw(cost_out, est_idx, g_prob, g_off, g_depth, g_dens, g_coding,
+                               near, interval, topk, raw)
         return g_cost, None, None, None, None
 
 
@@ -295,57 +320,72 @@ def _zeros_strided_like(t: torch.Tensor) -> torch.Tensor:
     return torch.empty_strided(t.size(), t.stride(), dtype=t.dtype, device=t.device).zero_()
 
 
+def _bp_fwd_raw(feat, points, projection, est_depth, est_dens, vs_z, h, w, mode, channels_first,
+                out=None, count=None):
+    """enqueue mvsd_backproject_fwd (aggregating modes); -> (volume logical [C,N], count)"""
+    v, c, fh, fw = feat.shape
+    t = est_depth.shape[1]
+    n = points.numel() // 3
+    dev = feat.device
+    sv, st, sy, sx = est_depth.stride()
+    shape = (c, n) if channels_first else (n, c)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous fp32 {shape} tensor (memory order of the volume)")
+    if count is None:
+        count = torch.empty((n,), dtype=torch.int32, device=dev)
+    elif count.numel() != n or count.dtype != torch.int32 or not count.is_contiguous():
+        raise ValueError("count must be a contiguous int32 [N] tensor")
+    _lib.call("mvsd_backproject_fwd", feat.data_ptr(), _code(feat.dtype), fh, fw,
+              points.data_ptr(), projection.data_ptr(), est_depth.data_ptr(),
+              est_dens.data_ptr(), sv, sy, sx, st, float(vs_z), mode, out.data_ptr(),
+              CHANNELS_FIRST if channels_first else CHANNELS_LAST, count.data_ptr(), None,
+              None, v, c, h, w, t, n, _stream())
+    return (out if channels_first else out.t()), count
+
+
+def _bp_bwd_raw(g_out, feat, points, projection, est_depth, est_dens, count, vs_z, h, w, mode,
+                channels_first):
+    """enqueue mvsd_backproject_bwd + mvsd_prob_norm_bwd; -> (dL/dfeat, dL/dest_dens)"""
+    v, c, fh, fw = feat.shape
+    t = est_depth.shape[1]
+    n = points.numel() // 3
+    sv, st, sy, sx = est_depth.stride()
+    g_out = g_out.float()
+    g_mem = g_out.contiguous() if channels_first else g_out.t().contiguous()
+    g_feat = _zeros_nhwc(v, c, fh, fw, torch.float32, feat.device)
+    g_pn = _zeros_strided_like(est_dens)
+    g_prob = _zeros_strided_like(est_dens)
+    _lib.call("mvsd_backproject_bwd", g_mem.data_ptr(),
+              CHANNELS_FIRST if channels_first else CHANNELS_LAST, mode, count.data_ptr(),
+              feat.data_ptr(), _code(feat.dtype), fh, fw, points.data_ptr(),
+              projection.data_ptr(), est_depth.data_ptr(), est_dens.data_ptr(),
+              sv, sy, sx, st, float(vs_z), g_feat.data_ptr(), g_pn.data_ptr(),
+              v, c, h, w, t, n, _stream())
+    _lib.call("mvsd_prob_norm_bwd", est_dens.data_ptr(), g_pn.data_ptr(), g_prob.data_ptr(),
+              sv, sy, sx, st, v, h, w, t, _stream())
+    g_feat = g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)
+    return g_feat, g_prob
+
+
 class _BackprojectAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, points, projection, est_depth, est_dens, vs_z, h, w, mode, channels_first,
                 out=None, count=None):
-        v, c, fh, fw = feat.shape
-        t = est_depth.shape[1]
-        n = points.numel() // 3
-        dev = feat.device
-        sv, st, sy, sx = est_depth.stride()
-        shape = (c, n) if channels_first else (n, c)
-        if out is None:
-            out = torch.empty(shape, dtype=torch.float32, device=dev)
-        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
-            raise ValueError(f"out must be a contiguous fp32 {shape} tensor (memory order of the volume)")
-        if count is None:
-            count = torch.empty((n,), dtype=torch.int32, device=dev)
-        elif count.numel() != n or count.dtype != torch.int32 or not count.is_contiguous():
-            raise ValueError("count must be a contiguous int32 [N] tensor")
-        _lib.call("mvsd_backproject_fwd", feat.data_ptr(), _code(feat.dtype), fh, fw,
-                  points.data_ptr(), projection.data_ptr(), est_depth.data_ptr(),
-                  est_dens.data_ptr(), sv, sy, sx, st, float(vs_z), mode, out.data_ptr(),
-                  CHANNELS_FIRST if channels_first else CHANNELS_LAST, count.data_ptr(), None,
-                  None, v, c, h, w, t, n, _stream())
+        res, count = _bp_fwd_raw(feat, points, projection, est_depth, est_dens, vs_z, h, w, mode,
+                                 channels_first, out, count)
         ctx.save_for_backward(feat, points, projection, est_depth, est_dens, count)
         ctx.consts = (float(vs_z), h, w, mode, channels_first)
         ctx.mark_non_differentiable(count)
-        res = out if channels_first else out.t()
         return res, count
 
     @staticmethod
     def backward(ctx, g_out, _g_count):
         feat, points, projection, est_depth, est_dens, count = ctx.saved_tensors
         vs_z, h, w, mode, channels_first = ctx.consts
-        v, c, fh, fw = feat.shape
-        t = est_depth.shape[1]
-        n = points.numel() // 3
-        sv, st, sy, sx = est_depth.stride()
-        g_out = g_out.float()
-        g_mem = g_out.contiguous() if channels_first else g_out.t().contiguous()
-        g_feat = _zeros_nhwc(v, c, fh, fw, torch.float32, feat.device)
-        g_pn = _zeros_strided_like(est_dens)
-        g_prob = _zeros_strided_like(est_dens)
-        _lib.call("mvsd_backproject_bwd", g_mem.data_ptr(),
-                  CHANNELS_FIRST if channels_first else CHANNELS_LAST, mode, count.data_ptr(),
-                  feat.data_ptr(), _code(feat.dtype), fh, fw, points.data_ptr(),
-                  projection.data_ptr(), est_depth.data_ptr(), est_dens.data_ptr(),
-                  sv, sy, sx, st, vs_z, g_feat.data_ptr(), g_pn.data_ptr(),
-                  v, c, h, w, t, n, _stream())
-        _lib.call("mvsd_prob_norm_bwd", est_dens.data_ptr(), g_pn.data_ptr(), g_prob.data_ptr(),
-                  sv, sy, sx, st, v, h, w, t, _stream())
-        g_feat = g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)
+        g_feat, g_prob = _bp_bwd_raw(g_out, feat, points, projection, est_depth, est_dens, count,
+                                     vs_z, h, w, mode, channels_first)
         return g_feat, None, None, None, g_prob, None, None, None, None, None, None, None
 
 

@@ -398,6 +398,10 @@ def hot_path(feature, img_meta, cost_regularization, *, near_far_range, num_dept
     neighbor_ids = get_nearest_pose_ids(w2c.inverse(), k)
     depth_interval = (near_far_range[1] - near_far_range[0]) / num_depth
     dvals = torch.as_tensor(depth_values_for(near_far_range, num_depth))
+    dev = feature.device                   # CPU for the checker; "cuda" only for tools/eager_gpu.py
+    if dev.type != "cpu":
+        projection, points, w2c, k_feat, neighbor_ids, dvals = (
+            t.to(dev) for t in (projection, points, w2c, k_feat, neighbor_ids, dvals))
     variance = plane_sweep_variance(feature, w2c, k_feat, neighbor_ids, dvals,
                                     training=training, view_subset=view_subset)
     if view_subset is not None:            # bounded CPU-baseline sample (bench.py)
