@@ -552,32 +552,43 @@ __device__ __forceinline__ void side_c(float* dst, const P4 (&cl)[G], const P4 (
   }
 }
 
-template <int G>
-struct HandoffSlot {                 // one stage: left and right weighted vectors, lane-private columns
-  P4 v[2][G][32];
+// One stage of a hand-off queue, lane-private columns.  NV = 2: the sender's bottom side already
+// weighted (left, right vectors); NV = 1: the sender's un-weighted contribution gw -- the receiver
+// applies the sender's two bottom weights, which it reads from the shared sample table anyway:
+// half the shared memory per stage, so the queue can be as deep as the run (NSTG = 8) and the
+// sending row never waits for the receiving one inside a plane.
+template <int G, int NV = 2>
+struct HandoffSlot {
+  P4 v[NV][G][32];
 };
 
 // One neighbour's scatter with the hand-off protocol.  send: give the bottom side to the
 // row below; recv: take the row above's bottom side into this row's top side.
-template <int G, bool FULL>
+template <int G, bool FULL, int NSTG, int NV>
 __device__ __forceinline__ void scatter_h(float* dst, const P4 (&gw)[G], const WarpSample& s,
                                           unsigned& id_top, P4 (&top)[G], unsigned& id_bot,
-                                          P4 (&bot)[G], bool send, HandoffSlot<G>* out_slot,
+                                          P4 (&bot)[G], bool send, HandoffSlot<G, NV>* out_slot,
                                           unsigned long long* out_full, unsigned long long* out_empty,
                                           unsigned& h_out, bool recv, float up_w10, float up_w11,
-                                          HandoffSlot<G>* in_slot, unsigned long long* in_full,
+                                          HandoffSlot<G, NV>* in_slot, unsigned long long* in_full,
                                           unsigned long long* in_empty, unsigned& h_in, int lane,
                                           int c0, int C) {
+  static_assert((NSTG & (NSTG - 1)) == 0, "stage count must be a power of two");
   // bottom side first: an early hand-off unblocks the warp below
   if (send) {
     const unsigned h = h_out++;
-    const unsigned stg = h & 1u, ph = (h >> 1) & 1u;
+    const unsigned stg = h & (unsigned)(NSTG - 1), ph = (h / (unsigned)NSTG) & 1u;
     mbar_wait(out_empty + stg, ph ^ 1u);
-    const u64 w10 = pk2(s.w10, s.w10), w11 = pk2(s.w11, s.w11);
+    if (NV == 2) {
+      const u64 w10 = pk2(s.w10, s.w10), w11 = pk2(s.w11, s.w11);
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      out_slot[stg].v[0][g][lane] = p4scale(gw[g], w10);
-      out_slot[stg].v[1][g][lane] = p4scale(gw[g], w11);
+      for (int g = 0; g < G; ++g) {
+        out_slot[stg].v[0][g][lane] = p4scale(gw[g], w10);
+        out_slot[stg].v[NV - 1][g][lane] = p4scale(gw[g], w11);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) out_slot[stg].v[0][g][lane] = gw[g];
     }
     mbar_arrive(out_full + stg);
   } else {
@@ -585,13 +596,23 @@ __device__ __forceinline__ void scatter_h(float* dst, const P4 (&gw)[G], const W
   }
   if (recv) {
     const unsigned h = h_in++;
-    const unsigned stg = h & 1u, ph = (h >> 1) & 1u;
+    const unsigned stg = h & (unsigned)(NSTG - 1), ph = (h / (unsigned)NSTG) & 1u;
     mbar_wait(in_full + stg, ph);
     P4 cl[G], cr[G];
+    if (NV == 2) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      cl[g] = in_slot[stg].v[0][g][lane];
-      cr[g] = in_slot[stg].v[1][g][lane];
+      for (int g = 0; g < G; ++g) {
+        cl[g] = in_slot[stg].v[0][g][lane];
+        cr[g] = in_slot[stg].v[NV - 1][g][lane];
+      }
+    } else {
+      const u64 u10 = pk2(up_w10, up_w10), u11 = pk2(up_w11, up_w11);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const P4 gu = in_slot[stg].v[0][g][lane];
+        cl[g] = p4scale(gu, u10);
+        cr[g] = p4scale(gu, u11);
+      }
     }
     mbar_arrive(in_empty + stg);
     const u64 w00 = pk2(s.w00, s.w00), w01 = pk2(s.w01, s.w01);
@@ -607,25 +628,26 @@ __device__ __forceinline__ void scatter_h(float* dst, const P4 (&gw)[G], const W
   }
 }
 
-template <int KMAX, int G>
+template <int KMAX, int G, int NSTG = 2, int NV = 2>
 struct HandoffCtx {                  // per-pixel hand-off decisions + the CTA's slots and barriers
+  static constexpr int kStages = NSTG, kVec = NV;
   bool send[KMAX], recv[KMAX];
   float up_w10[KMAX], up_w11[KMAX];
-  HandoffSlot<G> (*out_slot)[2];     // [KMAX][2] of the boundary below this row
-  unsigned long long (*out_full)[2], (*out_empty)[2];
-  HandoffSlot<G> (*in_slot)[2];      // boundary above this row
-  unsigned long long (*in_full)[2], (*in_empty)[2];
+  HandoffSlot<G, NV> (*out_slot)[NSTG];     // [KMAX][NSTG] of the boundary below this row
+  unsigned long long (*out_full)[NSTG], (*out_empty)[NSTG];
+  HandoffSlot<G, NV> (*in_slot)[NSTG];      // boundary above this row
+  unsigned long long (*in_full)[NSTG], (*in_empty)[NSTG];
   unsigned h_out[KMAX], h_in[KMAX];
   int lane;
 };
 
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1, bool HO = false>
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1, bool HO = false,
+          typename HOC = HandoffCtx<KMAX, G>>
 __device__ __forceinline__ void pixel_q(RunPending<KMAX, G>& pend, const WarpSample& s0,
                                         const WarpSample& s1, const TG* __restrict__ gp,
                                         const TIn* __restrict__ rp, const TIn* const (&nsrc)[KMAX],
                                         float* const (&ndst)[KMAX], uint32_t taddr, u64 inv_n2,
-                                        u64 two_inv_n2, int c0, int C,
-                                        HandoffCtx<KMAX, G>* ho = nullptr) {
+                                        u64 two_inv_n2, int c0, int C, HOC* ho = nullptr) {
   typename Raw<TG>::type graw[G];
   typename Raw<TIn>::type rraw[G];
 #pragma unroll
@@ -655,7 +677,7 @@ __device__ __forceinline__ void pixel_q(RunPending<KMAX, G>& pend, const WarpSam
   }
   if (V0) {
     if (HO) {
-      scatter_h<G, FULL>(ndst[0], gw0, s0, pend.id_top[0], pend.top[0], pend.id_bot[0], pend.bot[0],
+      scatter_h<G, FULL, HOC::kStages, HOC::kVec>(ndst[0], gw0, s0, pend.id_top[0], pend.top[0], pend.id_bot[0], pend.bot[0],
                          ho->send[0], ho->out_slot[0], ho->out_full[0], ho->out_empty[0], ho->h_out[0],
                          ho->recv[0], ho->up_w10[0], ho->up_w11[0], ho->in_slot[0], ho->in_full[0],
                          ho->in_empty[0], ho->h_in[0], ho->lane, c0, C);
@@ -667,7 +689,7 @@ __device__ __forceinline__ void pixel_q(RunPending<KMAX, G>& pend, const WarpSam
   if (V1) {
     constexpr int J = KMAX - 1;
     if (HO) {
-      scatter_h<G, FULL>(ndst[J], gw1, s1, pend.id_top[J], pend.top[J], pend.id_bot[J], pend.bot[J],
+      scatter_h<G, FULL, HOC::kStages, HOC::kVec>(ndst[J], gw1, s1, pend.id_top[J], pend.top[J], pend.id_bot[J], pend.bot[J],
                          ho->send[J], ho->out_slot[J], ho->out_full[J], ho->out_empty[J], ho->h_out[J],
                          ho->recv[J], ho->up_w10[J], ho->up_w11[J], ho->in_slot[J], ho->in_full[J],
                          ho->in_empty[J], ho->h_in[J], ho->lane, c0, C);
@@ -787,6 +809,215 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 }
 
 // ---------------------------------------------------------------------------
+// Software-pipelined lean kernel (tuning key 5 = 14).  ncu's per-warp picture of the lean kernel:
+// ~2260 cycles per pixel-plane = one L2 round trip for the 20 loads of the pixel (all issued
+// together, ~1000+ cycles under the RED traffic) followed by ~240 dependent-ish instructions at
+// ~4 cycles each, with only 3 warps per scheduler to overlap the two.  An L1 prefetch of the next
+// pixel hides the round trip but doubles the L1 tag traffic and is slower (measured twice).  Here
+// the loads of the NEXT pixel are issued into the raw-load registers as soon as the blend has
+// consumed the current ones, i.e. before the variance algebra, the tensor-memory update and the
+// scatter: the same registers, no extra L1 traffic, and the round trip overlaps ~60 % of the
+// pixel's instructions.  The pipeline runs across the planes of one sample-table fill.
+// ---------------------------------------------------------------------------
+template <typename TIn, typename TG, int G>
+struct PixelRaw {
+  typename Raw<TG>::type g[G];
+  typename Raw<TIn>::type r[G];
+  RawTaps<TIn, G> t0, t1;
+};
+
+template <typename TIn, typename TG, int KMAX, int G, bool FULL>
+__device__ __forceinline__ void issue_pixel_loads(PixelRaw<TIn, TG, G>& raw, const WarpSample* smp,
+                                                  const TG* __restrict__ gp, const TIn* __restrict__ rp,
+                                                  const TIn* const (&nsrc)[KMAX], int c0, int C) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const bool on = group_on<FULL>(c0, g, C);
+    raw.g[g] = on ? Raw<TG>::ld_stream_na(gp + 128 * g) : Raw<TG>::zero();
+    raw.r[g] = on ? Raw<TIn>::ld(rp + 128 * g) : Raw<TIn>::zero();
+  }
+  // only the four tap offsets are needed to issue the loads: the second 16 bytes of a sample
+  WarpSample a;
+  const uint4 q0 = reinterpret_cast<const uint4*>(smp)[1];
+  a.p00 = q0.x; a.p01 = q0.y; a.p10 = q0.z; a.p11 = q0.w;
+  if (q0.x != kNoSample) load_taps<TIn, G, FULL>(nsrc[0], a, c0, C, raw.t0);
+  if (KMAX == 2) {
+    const uint4 q1 = reinterpret_cast<const uint4*>(smp + (KMAX - 1))[1];
+    a.p00 = q1.x; a.p01 = q1.y; a.p10 = q1.z; a.p11 = q1.w;
+    if (q1.x != kNoSample) load_taps<TIn, G, FULL>(nsrc[KMAX - 1], a, c0, C, raw.t1);
+  }
+}
+
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1, bool HO = false,
+          typename HOC = HandoffCtx<KMAX, G>>
+__device__ __forceinline__ void pixel_q2(RunPending<KMAX, G>& pend, PixelRaw<TIn, TG, G>& raw,
+                                         const WarpSample& s0, const WarpSample& s1, bool has_next,
+                                         const WarpSample* smp_next, const TG* __restrict__ gp_next,
+                                         const TIn* __restrict__ rp_next, const TIn* const (&nsrc)[KMAX],
+                                         float* const (&ndst)[KMAX], uint32_t taddr, u64 inv_n2,
+                                         u64 two_inv_n2, int c0, int C, HOC* ho = nullptr) {
+  P4 w0[G], w1[G], gw0[G], gw1[G], ref[G], gv[G];
+  if (V0) blend_taps<TIn, G>(raw.t0, s0, w0);
+  if (V1) blend_taps<TIn, G>(raw.t1, s1, w1);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    ref[g] = p4from(raw.r[g]);
+    gv[g] = p4scale(p4from(raw.g[g]), two_inv_n2);
+  }
+  // the raw registers are free: the next pixel's round trip starts here
+  if (has_next) issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, smp_next, gp_next, rp_next, nsrc, c0, C);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    P4 mu = ref[g];
+    if (V0) mu = p4add(mu, w0[g]);
+    if (V1) mu = p4add(mu, w1[g]);
+    mu = p4scale(mu, inv_n2);
+    const uint32_t ta = taddr + 4u * (uint32_t)g;
+    tmem_st4(ta, p4fma(gv[g], p4sub(ref[g], mu), tmem_ld4(ta)));
+    if (V0) gw0[g] = p4mul(gv[g], p4sub(w0[g], mu));
+    if (V1) gw1[g] = p4mul(gv[g], p4sub(w1[g], mu));
+  }
+  if (V0) {
+    if (HO) {
+      scatter_h<G, FULL, HOC::kStages, HOC::kVec>(ndst[0], gw0, s0, pend.id_top[0], pend.top[0], pend.id_bot[0], pend.bot[0],
+                         ho->send[0], ho->out_slot[0], ho->out_full[0], ho->out_empty[0], ho->h_out[0],
+                         ho->recv[0], ho->up_w10[0], ho->up_w11[0], ho->in_slot[0], ho->in_full[0],
+                         ho->in_empty[0], ho->h_in[0], ho->lane, c0, C);
+    } else {
+      side_q<G, FULL>(ndst[0], gw0, s0.w00, s0.w01, s0.p00, s0.p01, pend.id_top[0], pend.top[0], c0, C);
+      side_q<G, FULL>(ndst[0], gw0, s0.w10, s0.w11, s0.p10, s0.p11, pend.id_bot[0], pend.bot[0], c0, C);
+    }
+  }
+  if (V1) {
+    constexpr int J = KMAX - 1;
+    if (HO) {
+      scatter_h<G, FULL, HOC::kStages, HOC::kVec>(ndst[J], gw1, s1, pend.id_top[J], pend.top[J], pend.id_bot[J], pend.bot[J],
+                         ho->send[J], ho->out_slot[J], ho->out_full[J], ho->out_empty[J], ho->h_out[J],
+                         ho->recv[J], ho->up_w10[J], ho->up_w11[J], ho->in_slot[J], ho->in_full[J],
+                         ho->in_empty[J], ho->h_in[J], ho->lane, c0, C);
+    } else {
+      side_q<G, FULL>(ndst[J], gw1, s1.w00, s1.w01, s1.p00, s1.p01, pend.id_top[J], pend.top[J], c0, C);
+      side_q<G, FULL>(ndst[J], gw1, s1.w10, s1.w11, s1.p10, s1.p11, pend.id_bot[J], pend.bot[J], c0, C);
+    }
+  }
+}
+
+// requires p.k == KMAX
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB>
+__global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq2_kernel(const SweepParams p) {
+  constexpr int kCols = kRun * G * 4;
+  __shared__ WarpSample s_tab[kRunRows][32];
+  __shared__ uint32_t s_tmem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RunCoord c = run_coord<G>(p, warp, lane);
+  const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);
+  if (c.y < p.H) {
+    const int C = p.C, HW = p.H * p.W;
+    const TIn* feat = static_cast<const TIn*>(p.feat);
+    const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const TIn* ref_row = feat + ref_off;
+    const size_t plane_stride = (size_t)HW * C;
+    const TG* g_d = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const bool one_chunk = p.slices == 1;
+    const unsigned pf_bytes = (unsigned)((one_chunk ? (size_t)c.npix * C : (size_t)min(128 * G, C - (c.c0 - 4 * lane))) *
+                                         sizeof(TG)) & ~15u;
+    const TG* pf_base = g_d - 4 * lane;
+    const bool pf_ok = pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
+                       ((plane_stride * sizeof(TG)) & 15) == 0;
+    auto prefetch_plane = [&](int d) {
+      if (!pf_ok || d >= p.D) return;
+      const TG* q = pf_base + (size_t)d * plane_stride;
+      if (one_chunk) {
+        if (lane == 0) prefetch_l2(q, pf_bytes);
+      } else if (lane < c.npix) {
+        prefetch_l2(q + (size_t)lane * C, pf_bytes);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < kPrefetchPlanes; ++d) prefetch_plane(d);
+
+    const TIn* nsrc[KMAX];
+    float* ndst[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+    }
+    const float inv_n = 1.0f / (float)(KMAX + 1);
+    const u64 inv_n2 = pk2(inv_n, inv_n);
+    const u64 two_inv_n2 = pk2(2.0f * inv_n, 2.0f * inv_n);
+    constexpr int spp = kRun * KMAX;
+    constexpr int ppf = 32 / spp > 0 ? 32 / spp : 1;
+
+#pragma unroll
+    for (int q = 0; q < kRun * G; ++q) tmem_st4(tbase + 4u * (uint32_t)q, p4zero());
+    tmem_wait_st();
+
+    PixelRaw<TIn, TG, G> raw;
+    for (int d0 = 0; d0 < p.D; d0 += ppf) {
+      __syncwarp();
+      fill_run_samples(s_tab[warp], p, c, d0, ppf, lane);
+      __syncwarp();
+      const int dend = min(p.D, d0 + ppf);
+      // pipeline prologue: first pixel of the first plane of this table fill
+      issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp], g_d, ref_row, nsrc, c.c0, C);
+      for (int d = d0; d < dend; ++d) {
+        prefetch_plane(d + kPrefetchPlanes);
+        tmem_wait_st();
+        RunPending<KMAX, G> pend;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          pend.id_top[j] = pend.id_bot[j] = kNoTap;
+#pragma unroll
+          for (int g = 0; g < G; ++g) pend.top[j][g] = pend.bot[j][g] = p4zero();
+        }
+        const WarpSample* tab = s_tab[warp] + (d - d0) * spp;
+        const bool more_planes = d + 1 < dend;
+#pragma unroll 1
+        for (int i = 0; i < c.npix; ++i) {
+          const WarpSample s0 = tab[i * KMAX];
+          const WarpSample s1 = tab[i * KMAX + (KMAX - 1)];
+          const bool v0 = s0.p00 != kNoSample;
+          const bool v1 = KMAX == 2 && s1.p00 != kNoSample;
+          const bool in_run = i + 1 < c.npix;
+          const bool has_next = in_run || more_planes;
+          const WarpSample* smp_next = in_run ? tab + (i + 1) * KMAX : tab + spp;
+          const TG* gp_next = in_run ? g_d + (i + 1) * C : g_d + plane_stride;
+          const TIn* rp_next = in_run ? ref_row + (i + 1) * C : ref_row;
+          const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
+          if (v0 && v1)
+            pixel_q2<TIn, TG, KMAX, G, FULL, true, true>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C);
+          else if (v0)
+            pixel_q2<TIn, TG, KMAX, G, FULL, true, false>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C);
+          else if (v1)
+            pixel_q2<TIn, TG, KMAX, G, FULL, false, true>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C);
+          else
+            pixel_q2<TIn, TG, KMAX, G, FULL, false, false>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C);
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          flush_open_p<G, FULL>(ndst[j], pend.id_top[j], pend.top[j], c.c0, C);
+          flush_open_p<G, FULL>(ndst[j], pend.id_bot[j], pend.bot[j], c.c0, C);
+        }
+        g_d += plane_stride;
+      }
+    }
+    tmem_wait_st();
+    float* dst = p.g_feat + ref_off;
+    for (int i = 0; i < c.npix; ++i) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const P4 acc = tmem_ld4(tbase + 4u * (uint32_t)(i * G + g));
+        if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, acc);
+      }
+    }
+  }
+  tmem_free_cta<kCols>(&s_tmem, warp);
+}
+
+// ---------------------------------------------------------------------------
 // Row-handoff variant (tuning key 5 = 8).  The lean kernel is bound by the RED stream
 // (3.6 GB against a 5.7 TB/s ceiling): a further cut has to merge across image rows.
 // The four warps of a CTA own four consecutive rows of the same 8-pixel run; the bottom
@@ -798,17 +1029,25 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 // merge-or-flush step.  Replay (tools/red_merge_sim.py): 3.5 -> 2.7 GB of RED payload.
 // ---------------------------------------------------------------------------
 // requires p.k == KMAX
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB>
+template <int KMAX, int G, int NSTG, int NV>
+constexpr size_t runh_slot_bytes() { return sizeof(HandoffSlot<G, NV>) * (kRunRows - 1) * KMAX * NSTG; }
+
+// NSTG stages of NV vectors per (row boundary, neighbour): <2, 2> is the first version (tuning 5 = 8),
+// <4, 1> (5 = 9) and <8, 1> (5 = 10) the deeper queues of un-weighted contributions.  The slots live in
+// dynamic shared memory (48 KB for <8, 1> with G = 2, k = 2).
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, int NSTG = 2, int NV = 2>
 __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const SweepParams p) {
   constexpr int kCols = kRun * G * 4;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  typedef HandoffSlot<G, NV> (*SlotArr)[KMAX][NSTG];
+  SlotArr s_slot = reinterpret_cast<SlotArr>(s_dyn);          // [kRunRows - 1][KMAX][NSTG]
   __shared__ WarpSample s_tab[kRunRows][32];
-  __shared__ __align__(16) HandoffSlot<G> s_slot[kRunRows - 1][KMAX][2];
-  __shared__ __align__(8) unsigned long long s_full[kRunRows - 1][KMAX][2];
-  __shared__ __align__(8) unsigned long long s_empty[kRunRows - 1][KMAX][2];
+  __shared__ __align__(8) unsigned long long s_full[kRunRows - 1][KMAX][NSTG];
+  __shared__ __align__(8) unsigned long long s_empty[kRunRows - 1][KMAX][NSTG];
   __shared__ uint32_t s_tmem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const RunCoord c = run_coord<G>(p, warp, lane);
-  if (threadIdx.x < (kRunRows - 1) * KMAX * 2) {
+  if (threadIdx.x < (kRunRows - 1) * KMAX * NSTG) {
     mbar_init(&s_full[0][0][0] + threadIdx.x, 32);
     mbar_init(&s_empty[0][0][0] + threadIdx.x, 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -856,7 +1095,8 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const
   constexpr int ppf = 32 / spp > 0 ? 32 / spp : 1;
   const int wdn = min(warp + 1, kRunRows - 1), wup = max(warp - 1, 0);
   const int bo = min(warp, kRunRows - 2), bi = max(warp - 1, 0);     // boundary below / above this row
-  HandoffCtx<KMAX, G> ho;
+  typedef HandoffCtx<KMAX, G, NSTG, NV> HOC;
+  HOC ho;
   ho.out_slot = s_slot[bo]; ho.out_full = s_full[bo]; ho.out_empty = s_empty[bo];
   ho.in_slot = s_slot[bi]; ho.in_full = s_full[bi]; ho.in_empty = s_empty[bi];
   ho.lane = lane;
@@ -925,13 +1165,13 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const
         const TIn* rp = ref_row + i * C;
         const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
         if (v0 && v1)
-          pixel_q<TIn, TG, KMAX, G, FULL, true, true, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+          pixel_q<TIn, TG, KMAX, G, FULL, true, true, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
         else if (v0)
-          pixel_q<TIn, TG, KMAX, G, FULL, true, false, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+          pixel_q<TIn, TG, KMAX, G, FULL, true, false, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
         else if (v1)
-          pixel_q<TIn, TG, KMAX, G, FULL, false, true, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+          pixel_q<TIn, TG, KMAX, G, FULL, false, true, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
         else
-          pixel_q<TIn, TG, KMAX, G, FULL, false, false, true>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+          pixel_q<TIn, TG, KMAX, G, FULL, false, false, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
       }
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
@@ -942,6 +1182,255 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const
     }
   }
   if (active) {
+    tmem_wait_st();
+    float* dst = p.g_feat + ref_off;
+    for (int i = 0; i < c.npix; ++i) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const P4 acc = tmem_ld4(tbase + 4u * (uint32_t)(i * G + g));
+        if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, acc);
+      }
+    }
+  }
+  tmem_free_cta<kCols>(&s_tmem, warp);
+}
+
+// ---------------------------------------------------------------------------
+// Row hand-off with the decisions taken at table-fill time (tuning key 5 = 11: 2 stages,
+// 12: 4 stages).  ncu on sweep_bwd_runh: 366 M warp instructions against 274 M for the lean
+// kernel and a CTA barrier every two planes -- the per-pixel send / receive tests read the
+// sample tables of the rows above and below (six extra 16-byte shared loads and ~30 ALU
+// instructions per pixel), which is also what forces the four warps to refill their tables
+// in lock step.  Here the lane that computes a sample also computes the samples of the two
+// adjacent rows (same function, same inputs: the same bits the other warp gets) and stores
+// the outcome as four flag bits next to the sample; a warp then reads only its own table,
+// the per-pixel decision is a byte load, and the only coupling left between the warps of a
+// CTA is the hand-off queue itself.
+// ---------------------------------------------------------------------------
+constexpr unsigned kHoSend = 1u, kHoRecv = 2u, kHoNzLeft = 4u, kHoNzRight = 8u;
+
+__device__ __forceinline__ void fill_run_samples_ho(WarpSample* tab, unsigned char* flg,
+                                                    const SweepParams& p, const RunCoord& c, int d0,
+                                                    int ppf, int lane, bool has_up, bool has_dn) {
+  const int k = p.k, spp = kRun * k;
+  if (lane < ppf * spp) {
+    const int dd = lane / spp, rem = lane - dd * spp;
+    const int i = rem / k, j = rem - i * k;
+    const int d = d0 + dd;
+    WarpSample s;
+    s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
+    s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
+    unsigned f = 0u;
+    if (d < p.D && i < c.npix) {
+      const float* m = p.hom + ((size_t)c.v * k + j) * 12;
+      float mm[12];
+#pragma unroll
+      for (int t = 0; t < 12; ++t) mm[t] = __ldg(m + t);
+      const float depth = __ldg(p.depth + (size_t)c.v * p.D + d);
+      const float x = (float)(c.x0 + i);
+      s = make_warp_sample(mm, x, (float)c.y, depth, p.H, p.W, p.C);
+      if (s.p00 != kNoSample) {
+        if (has_dn) {
+          const WarpSample dn = make_warp_sample(mm, x, (float)(c.y + 1), depth, p.H, p.W, p.C);
+          if (dn.p00 != kNoSample && dn.p00 == s.p10 && dn.p01 == s.p11) f |= kHoSend;
+        }
+        if (has_up) {
+          const WarpSample up = make_warp_sample(mm, x, (float)(c.y - 1), depth, p.H, p.W, p.C);
+          if (up.p00 != kNoSample && up.p10 == s.p00 && up.p11 == s.p01) {
+            f |= kHoRecv;
+            if (s.w00 != 0.f || up.w10 != 0.f) f |= kHoNzLeft;
+            if (s.w01 != 0.f || up.w11 != 0.f) f |= kHoNzRight;
+          }
+        }
+      }
+    }
+    tab[lane] = s;
+    flg[lane] = (unsigned char)f;
+  }
+}
+
+// L1 prefetch of everything the NEXT pixel of the run will load (taps of both neighbours, upstream
+// gradient, reference feature): one 128-byte line per lane.  The hand-off kernel is not bound by
+// the RED stream any more (2.7 GB at 3.4 TB/s) but by the serial chain "wait for one L2 round trip,
+// then ~300 instructions" of each of its 12 warps per SM; with the lines already in L1 the round
+// trip of the next pixel overlaps this pixel's arithmetic and scatter.  FULL slices only (every
+// line of the slice is inside the tensor).
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
+template <typename TIn, typename TG, int KMAX, int G>
+__device__ __forceinline__ void prefetch_pixel_l1(const WarpSample* smp, const TIn* const (&nsrc)[KMAX],
+                                                  const TG* gp, const TIn* rp, int lane) {
+  constexpr int kTapLineElems = 128 / (int)sizeof(TIn);
+  constexpr int kTapLines = (128 * G) / kTapLineElems;          // lines per tap of this warp's slice
+  constexpr int kGLineElems = 128 / (int)sizeof(TG);
+  constexpr int kGLines = (128 * G) / kGLineElems;
+  const int j = lane >> 4, tap = (lane >> 2) & 3, l = lane & 3;
+  if (j < KMAX && l < kTapLines) {
+    const unsigned off = reinterpret_cast<const unsigned*>(smp + j)[4 + tap];
+    if (off != kNoSample)
+      prefetch_l1(at(j == 0 ? nsrc[0] : nsrc[KMAX - 1], off) + (kTapLineElems * l - 4 * lane));
+  }
+  // lanes [0, kGLines): gradient lines; the next kTapLines lanes: reference-feature lines
+  if (lane < kGLines) prefetch_l1(gp + (kGLineElems * lane - 4 * lane));
+  else if (lane < kGLines + kTapLines) prefetch_l1(rp + (kTapLineElems * (lane - kGLines) - 4 * lane));
+}
+
+// requires p.k == KMAX
+// SP = true: software-pipelined loads as in sweep_bwd_runq2 (tuning key 5 = 15).
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, int NSTG, bool PF = false, bool SP = false>
+__global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runf_kernel(const SweepParams p) {
+  constexpr int kCols = kRun * G * 4;
+  constexpr int NV = 2;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  typedef HandoffSlot<G, NV> (*SlotArr)[KMAX][NSTG];
+  SlotArr s_slot = reinterpret_cast<SlotArr>(s_dyn);          // [kRunRows - 1][KMAX][NSTG]
+  __shared__ WarpSample s_tab[kRunRows][32];
+  __shared__ unsigned char s_flg[kRunRows][32];
+  __shared__ __align__(8) unsigned long long s_full[kRunRows - 1][KMAX][NSTG];
+  __shared__ __align__(8) unsigned long long s_empty[kRunRows - 1][KMAX][NSTG];
+  __shared__ uint32_t s_tmem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RunCoord c = run_coord<G>(p, warp, lane);
+  if (threadIdx.x < (kRunRows - 1) * KMAX * NSTG) {
+    mbar_init(&s_full[0][0][0] + threadIdx.x, 32);
+    mbar_init(&s_empty[0][0][0] + threadIdx.x, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);     // contains the CTA barriers
+  if (c.y < p.H) {
+    const int C = p.C, HW = p.H * p.W;
+    const TIn* feat = static_cast<const TIn*>(p.feat);
+    const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const TIn* ref_row = feat + ref_off;
+    const size_t plane_stride = (size_t)HW * C;
+    const TG* g_d = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const bool one_chunk = p.slices == 1;
+    const unsigned pf_bytes = (unsigned)((one_chunk ? (size_t)c.npix * C : (size_t)min(128 * G, C - (c.c0 - 4 * lane))) *
+                                         sizeof(TG)) & ~15u;
+    const TG* pf_base = g_d - 4 * lane;
+    const bool pf_ok = pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
+                       ((plane_stride * sizeof(TG)) & 15) == 0;
+    auto prefetch_plane = [&](int d) {
+      if (!pf_ok || d >= p.D) return;
+      const TG* q = pf_base + (size_t)d * plane_stride;
+      if (one_chunk) {
+        if (lane == 0) prefetch_l2(q, pf_bytes);
+      } else if (lane < c.npix) {
+        prefetch_l2(q + (size_t)lane * C, pf_bytes);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < kPrefetchPlanes; ++d) prefetch_plane(d);
+
+    const TIn* nsrc[KMAX];
+    float* ndst[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+    }
+    const float inv_n = 1.0f / (float)(KMAX + 1);
+    const u64 inv_n2 = pk2(inv_n, inv_n);
+    const u64 two_inv_n2 = pk2(2.0f * inv_n, 2.0f * inv_n);
+    constexpr int spp = kRun * KMAX;
+    constexpr int ppf = 32 / spp > 0 ? 32 / spp : 1;
+    const bool has_up = warp > 0;
+    const bool has_dn = warp + 1 < kRunRows && c.y + 1 < p.H;
+    const int bo = min(warp, kRunRows - 2), bi = max(warp - 1, 0);     // boundary below / above this row
+    typedef HandoffCtx<KMAX, G, NSTG, NV> HOC;
+    HOC ho;
+    ho.out_slot = s_slot[bo]; ho.out_full = s_full[bo]; ho.out_empty = s_empty[bo];
+    ho.in_slot = s_slot[bi]; ho.in_full = s_full[bi]; ho.in_empty = s_empty[bi];
+    ho.lane = lane;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) ho.h_out[j] = ho.h_in[j] = 0u;
+
+#pragma unroll
+    for (int q = 0; q < kRun * G; ++q) tmem_st4(tbase + 4u * (uint32_t)q, p4zero());
+    tmem_wait_st();
+
+    PixelRaw<TIn, TG, G> raw;
+    for (int d0 = 0; d0 < p.D; d0 += ppf) {
+      __syncwarp();
+      fill_run_samples_ho(s_tab[warp], s_flg[warp], p, c, d0, ppf, lane, has_up, has_dn);
+      __syncwarp();
+      const int dend = min(p.D, d0 + ppf);
+      if (SP) issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp], g_d, ref_row, nsrc, c.c0, C);
+      for (int d = d0; d < dend; ++d) {
+        prefetch_plane(d + kPrefetchPlanes);
+        tmem_wait_st();
+        RunPending<KMAX, G> pend;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          pend.id_top[j] = pend.id_bot[j] = kNoTap;
+#pragma unroll
+          for (int g = 0; g < G; ++g) pend.top[j][g] = pend.bot[j][g] = p4zero();
+        }
+        const int toff = (d - d0) * spp;
+        const WarpSample* tab = s_tab[warp] + toff;
+        const unsigned char* flg = s_flg[warp] + toff;
+#pragma unroll 1
+        for (int i = 0; i < c.npix; ++i) {
+          if (PF && FULL) {
+            if (i + 1 < c.npix)
+              prefetch_pixel_l1<TIn, TG, KMAX, G>(tab + (i + 1) * KMAX, nsrc, g_d + (i + 1) * C,
+                                                  ref_row + (i + 1) * C, lane);
+            else if (d + 1 < dend)          // first pixel of the next plane (its table is already filled)
+              prefetch_pixel_l1<TIn, TG, KMAX, G>(tab + spp, nsrc, g_d + plane_stride, ref_row, lane);
+          }
+          const WarpSample s0 = tab[i * KMAX];
+          const WarpSample s1 = tab[i * KMAX + (KMAX - 1)];
+          const bool v0 = s0.p00 != kNoSample;
+          const bool v1 = KMAX == 2 && s1.p00 != kNoSample;
+#pragma unroll
+          for (int j = 0; j < KMAX; ++j) {
+            const unsigned f = flg[i * KMAX + j];
+            ho.send[j] = (f & kHoSend) != 0u;
+            ho.recv[j] = (f & kHoRecv) != 0u;
+            // scatter_h only tests these against zero (NV == 2: the sender pre-weights)
+            ho.up_w10[j] = (f & kHoNzLeft) ? 1.f : 0.f;
+            ho.up_w11[j] = (f & kHoNzRight) ? 1.f : 0.f;
+          }
+          const TG* gp = g_d + i * C;
+          const TIn* rp = ref_row + i * C;
+          const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
+          if (SP) {
+            const bool in_run = i + 1 < c.npix;
+            const bool has_next = in_run || d + 1 < dend;
+            const WarpSample* smp_next = in_run ? tab + (i + 1) * KMAX : tab + spp;
+            const TG* gp_next = in_run ? gp + C : g_d + plane_stride;
+            const TIn* rp_next = in_run ? rp + C : ref_row;
+            if (v0 && v1)
+              pixel_q2<TIn, TG, KMAX, G, FULL, true, true, true, HOC>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+            else if (v0)
+              pixel_q2<TIn, TG, KMAX, G, FULL, true, false, true, HOC>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+            else if (v1)
+              pixel_q2<TIn, TG, KMAX, G, FULL, false, true, true, HOC>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+            else
+              pixel_q2<TIn, TG, KMAX, G, FULL, false, false, true, HOC>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+            continue;
+          }
+          if (v0 && v1)
+            pixel_q<TIn, TG, KMAX, G, FULL, true, true, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+          else if (v0)
+            pixel_q<TIn, TG, KMAX, G, FULL, true, false, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+          else if (v1)
+            pixel_q<TIn, TG, KMAX, G, FULL, false, true, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+          else
+            pixel_q<TIn, TG, KMAX, G, FULL, false, false, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          flush_open_p<G, FULL>(ndst[j], pend.id_top[j], pend.top[j], c.c0, C);
+          flush_open_p<G, FULL>(ndst[j], pend.id_bot[j], pend.bot[j], c.c0, C);
+        }
+        g_d += plane_stride;
+      }
+    }
     tmem_wait_st();
     float* dst = p.g_feat + ref_off;
     for (int i = 0; i < c.npix; ++i) {
@@ -974,9 +1463,38 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   { const int flag = tuning(6); cudaMemcpyToSymbolAsync(c_exp_nored, &flag, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
 #endif
 #if MVSD_KRUN == 8
+#define MVSD_RUNH(KM, GG, FU, NS, NVV)                                                      \
+  do {                                                                                    \
+    auto kern = sweep_bwd_runh_kernel<TIn, TG, KM, GG, FU, 3, NS, NVV>;                    \
+    constexpr size_t dyn = runh_slot_bytes<KM, GG, NS, NVV>();                            \
+    static bool attr_set = false;                                                         \
+    if (!attr_set) {                                                                      \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);  \
+      attr_set = true;                                                                    \
+    }                                                                                     \
+    kern<<<grid, kRunThreads, dyn, st>>>(p);                                              \
+  } while (0)
+#define MVSD_RUNF(KM, GG, FU, NS, ...)                                                      \
+  do {                                                                                    \
+    auto kern = sweep_bwd_runf_kernel<TIn, TG, KM, GG, FU, 3, NS, ##__VA_ARGS__>;          \
+    constexpr size_t dyn = runh_slot_bytes<KM, GG, NS, 2>();                              \
+    static bool attr_set = false;                                                         \
+    if (!attr_set) {                                                                      \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);  \
+      attr_set = true;                                                                    \
+    }                                                                                     \
+    kern<<<grid, kRunThreads, dyn, st>>>(p);                                              \
+  } while (0)
 #define MVSD_RUN(KM, GG, FU)                                                              \
   do {                                                                                    \
-    if (tuning(5) == 8) sweep_bwd_runh_kernel<TIn, TG, KM, GG, FU, 3><<<grid, kRunThreads, 0, st>>>(p); \
+    if (tuning(5) == 8) MVSD_RUNH(KM, GG, FU, 2, 2);                                         \
+    else if (tuning(5) == 9) MVSD_RUNH(KM, GG, FU, 4, 1);                                    \
+    else if (tuning(5) == 10) MVSD_RUNH(KM, GG, FU, 8, 1);                                   \
+    else if (tuning(5) == 11) MVSD_RUNF(KM, GG, FU, 2);                                      \
+    else if (tuning(5) == 12) MVSD_RUNF(KM, GG, FU, 4);                                      \
+    else if (tuning(5) == 13) MVSD_RUNF(KM, GG, FU, 2, true);                                \
+    else if (tuning(5) == 15) MVSD_RUNF(KM, GG, FU, 2, false, true);                         \
+    else if (tuning(5) == 14) sweep_bwd_runq2_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (lean) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, false><<<grid, kRunThreads, 0, st>>>(p); \
@@ -995,6 +1513,8 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
     else { if (full) MVSD_RUN(2, 1, true); else MVSD_RUN(2, 1, false); }
   }
 #undef MVSD_RUN
+#undef MVSD_RUNH
+#undef MVSD_RUNF
   count_launch();
   return check_launch("plane_sweep_bwd(run)");
 }
