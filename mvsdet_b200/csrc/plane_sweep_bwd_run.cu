@@ -809,7 +809,8 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 }
 
 // ---------------------------------------------------------------------------
-// Software-pipelined lean kernel (tuning key 5 = 14).  ncu's per-warp picture of the lean kernel:
+// Software-pipelined lean kernel (default since round 1f; tuning key 5 = 7 selects the un-pipelined
+// sweep_bwd_runq above).  ncu's per-warp picture of the lean kernel:
 // ~2260 cycles per pixel-plane = one L2 round trip for the 20 loads of the pixel (all issued
 // together, ~1000+ cycles under the RED traffic) followed by ~240 dependent-ish instructions at
 // ~4 cycles each, with only 3 warps per scheduler to overlap the two.  An L1 prefetch of the next
@@ -1444,6 +1445,300 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runf_kernel(const
   tmem_free_cta<kCols>(&s_tmem, warp);
 }
 
+// ---------------------------------------------------------------------------
+// Slim hand-off kernel with software-pipelined loads (tuning key 5 = 16).  sweep_bwd_runf with the
+// pipelining of sweep_bwd_runq2 needs ~190 registers (168 + 80 bytes of spills: slower).  Same
+// algorithm on a register diet: the hand-off queues are addressed with 32-bit shared-space
+// addresses computed from two bases (was six 64-bit pointers), the sample of a pixel is re-read
+// from the table where it is used (weights at the blend, weights + offsets at the scatter)
+// instead of living in 16 registers across the loads of the next pixel, and the per-pixel
+// decisions stay packed in their flag byte.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_a(unsigned a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned a, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" :: "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sts_p4(unsigned a, P4 v) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" :: "r"(a), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ P4 lds_p4(unsigned a) {
+  P4 v;
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(unsigned a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
+template <int KMAX>
+struct HoLite {
+  unsigned slot_out, slot_in;    // shared address of (boundary below / above, neighbour 0, stage 0), this lane's column
+  unsigned bar_out, bar_in;      // shared address of the boundary's first {full, empty} barrier pair
+  unsigned h_out[KMAX], h_in[KMAX];
+};
+
+// one neighbour (J) of one pixel: wq = (w00, w01, w10, w11), oq = (p00, p01, p10, p11)
+template <int G, bool FULL, int NSTG, int J, int KMAX>
+__device__ __forceinline__ void scatter_hl(float* dst, const P4 (&gw)[G], float4 wq, uint4 oq,
+                                           unsigned& id_top, P4 (&top)[G], unsigned& id_bot,
+                                           P4 (&bot)[G], unsigned flags, HoLite<KMAX>& ho, int c0, int C) {
+  static_assert((NSTG & (NSTG - 1)) == 0, "stage count must be a power of two");
+  constexpr unsigned kVec = 512u;                     // 32 lanes x 16 bytes
+  constexpr unsigned kSlot = 2u * G * kVec;           // left + right weighted vectors
+  constexpr unsigned jslot = (unsigned)J * NSTG * kSlot, jbar = (unsigned)J * NSTG * 16u;
+  if (flags & kHoSend) {
+    const unsigned h = ho.h_out[J]++;
+    const unsigned stg = h & (unsigned)(NSTG - 1), ph = (h / (unsigned)NSTG) & 1u;
+    const unsigned bar = ho.bar_out + jbar + stg * 16u;
+    mbar_wait_a(bar + 8u, ph ^ 1u);                   // slot empty
+    const unsigned a = ho.slot_out + jslot + stg * kSlot;
+    const u64 w10 = pk2(wq.z, wq.z), w11 = pk2(wq.w, wq.w);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      sts_p4(a + (unsigned)g * kVec, p4scale(gw[g], w10));
+      sts_p4(a + (unsigned)(G + g) * kVec, p4scale(gw[g], w11));
+    }
+    mbar_arrive_a(bar);                               // slot full
+  } else {
+    side_q<G, FULL>(dst, gw, wq.z, wq.w, oq.z, oq.w, id_bot, bot, c0, C);
+  }
+  if (flags & kHoRecv) {
+    const unsigned h = ho.h_in[J]++;
+    const unsigned stg = h & (unsigned)(NSTG - 1), ph = (h / (unsigned)NSTG) & 1u;
+    const unsigned bar = ho.bar_in + jbar + stg * 16u;
+    mbar_wait_a(bar, ph);
+    const unsigned a = ho.slot_in + jslot + stg * kSlot;
+    P4 cl[G], cr[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cl[g] = lds_p4(a + (unsigned)g * kVec);
+      cr[g] = lds_p4(a + (unsigned)(G + g) * kVec);
+    }
+    mbar_arrive_a(bar + 8u);
+    const u64 w00 = pk2(wq.x, wq.x), w01 = pk2(wq.y, wq.y);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cl[g] = p4fma(gw[g], w00, cl[g]);
+      cr[g] = p4fma(gw[g], w01, cr[g]);
+    }
+    side_c<G, FULL>(dst, cl, cr, (flags & kHoNzLeft) != 0u, (flags & kHoNzRight) != 0u, oq.x, oq.y,
+                    id_top, top, c0, C);
+  } else {
+    side_q<G, FULL>(dst, gw, wq.x, wq.y, oq.x, oq.y, id_top, top, c0, C);
+  }
+}
+
+template <typename TIn, int G>
+__device__ __forceinline__ void blend_taps_w(const RawTaps<TIn, G>& r, float4 wq, P4 (&wv)[G]) {
+  WarpSample s;
+  s.w00 = wq.x; s.w01 = wq.y; s.w10 = wq.z; s.w11 = wq.w;
+  blend_taps<TIn, G>(r, s, wv);
+}
+
+// sa: shared address of this pixel's first sample (32 bytes per sample)
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int NSTG, bool V0, bool V1>
+__device__ __forceinline__ void pixel_q3(RunPending<KMAX, G>& pend, PixelRaw<TIn, TG, G>& raw, unsigned sa,
+                                         unsigned flags0, unsigned flags1, bool has_next,
+                                         const WarpSample* smp_next, const TG* __restrict__ gp_next,
+                                         const TIn* __restrict__ rp_next, const TIn* const (&nsrc)[KMAX],
+                                         float* const (&ndst)[KMAX], uint32_t taddr, u64 inv_n2,
+                                         u64 two_inv_n2, int c0, int C, HoLite<KMAX>& ho) {
+  constexpr unsigned kS1 = 32u * (KMAX - 1);
+  P4 w0[G], w1[G], gw0[G], gw1[G], ref[G], gv[G];
+  if (V0) blend_taps_w<TIn, G>(raw.t0, lds_f4(sa), w0);
+  if (V1) blend_taps_w<TIn, G>(raw.t1, lds_f4(sa + kS1), w1);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    ref[g] = p4from(raw.r[g]);
+    gv[g] = p4scale(p4from(raw.g[g]), two_inv_n2);
+  }
+  if (has_next) issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, smp_next, gp_next, rp_next, nsrc, c0, C);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    P4 mu = ref[g];
+    if (V0) mu = p4add(mu, w0[g]);
+    if (V1) mu = p4add(mu, w1[g]);
+    mu = p4scale(mu, inv_n2);
+    const uint32_t ta = taddr + 4u * (uint32_t)g;
+    tmem_st4(ta, p4fma(gv[g], p4sub(ref[g], mu), tmem_ld4(ta)));
+    if (V0) gw0[g] = p4mul(gv[g], p4sub(w0[g], mu));
+    if (V1) gw1[g] = p4mul(gv[g], p4sub(w1[g], mu));
+  }
+  if (V0)
+    scatter_hl<G, FULL, NSTG, 0, KMAX>(ndst[0], gw0, lds_f4(sa), lds_u4(sa + 16u), pend.id_top[0], pend.top[0],
+                                       pend.id_bot[0], pend.bot[0], flags0, ho, c0, C);
+  if (V1)
+    scatter_hl<G, FULL, NSTG, KMAX - 1, KMAX>(ndst[KMAX - 1], gw1, lds_f4(sa + kS1), lds_u4(sa + kS1 + 16u),
+                                              pend.id_top[KMAX - 1], pend.top[KMAX - 1], pend.id_bot[KMAX - 1],
+                                              pend.bot[KMAX - 1], flags1, ho, c0, C);
+}
+
+// requires p.k == KMAX
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, int NSTG>
+__global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const SweepParams p) {
+  constexpr int kCols = kRun * G * 4;
+  constexpr unsigned kSlot = 2u * G * 512u;
+  extern __shared__ __align__(16) unsigned char s_dyn[];          // [kRunRows - 1][KMAX][NSTG] slots
+  __shared__ WarpSample s_tab[kRunRows][32];
+  __shared__ unsigned char s_flg[kRunRows][32];
+  __shared__ __align__(8) unsigned long long s_bar[kRunRows - 1][KMAX][NSTG][2];   // {full, empty}
+  __shared__ uint32_t s_tmem;
+  static_assert(sizeof(WarpSample) == 32, "sample table stride");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RunCoord c = run_coord<G>(p, warp, lane);
+  if (threadIdx.x < (kRunRows - 1) * KMAX * NSTG * 2) {
+    mbar_init(&s_bar[0][0][0][0] + threadIdx.x, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);     // contains the CTA barriers
+  if (c.y < p.H) {
+    const int C = p.C, HW = p.H * p.W;
+    const TIn* feat = static_cast<const TIn*>(p.feat);
+    const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const TIn* ref_row = feat + ref_off;
+    const size_t plane_stride = (size_t)HW * C;
+    const TG* g_d = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const bool one_chunk = p.slices == 1;
+    const unsigned pf_bytes = (unsigned)((one_chunk ? (size_t)c.npix * C : (size_t)min(128 * G, C - (c.c0 - 4 * lane))) *
+                                         sizeof(TG)) & ~15u;
+    const TG* pf_base = g_d - 4 * lane;
+    const bool pf_ok = pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
+                       ((plane_stride * sizeof(TG)) & 15) == 0;
+    auto prefetch_plane = [&](int d) {
+      if (!pf_ok || d >= p.D) return;
+      const TG* q = pf_base + (size_t)d * plane_stride;
+      if (one_chunk) {
+        if (lane == 0) prefetch_l2(q, pf_bytes);
+      } else if (lane < c.npix) {
+        prefetch_l2(q + (size_t)lane * C, pf_bytes);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < kPrefetchPlanes; ++d) prefetch_plane(d);
+
+    const TIn* nsrc[KMAX];
+    float* ndst[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+    }
+    const float inv_n = 1.0f / (float)(KMAX + 1);
+    const u64 inv_n2 = pk2(inv_n, inv_n);
+    const u64 two_inv_n2 = pk2(2.0f * inv_n, 2.0f * inv_n);
+    constexpr int spp = kRun * KMAX;
+    constexpr int ppf = 32 / spp > 0 ? 32 / spp : 1;
+    const bool has_up = warp > 0;
+    const bool has_dn = warp + 1 < kRunRows && c.y + 1 < p.H;
+    const int bo = min(warp, kRunRows - 2), bi = max(warp - 1, 0);     // boundary below / above this row
+    HoLite<KMAX> ho;
+    ho.slot_out = smem_u32(s_dyn) + (unsigned)(bo * KMAX * NSTG) * kSlot + (unsigned)lane * 16u;
+    ho.slot_in = smem_u32(s_dyn) + (unsigned)(bi * KMAX * NSTG) * kSlot + (unsigned)lane * 16u;
+    ho.bar_out = smem_u32(&s_bar[bo][0][0][0]);
+    ho.bar_in = smem_u32(&s_bar[bi][0][0][0]);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) ho.h_out[j] = ho.h_in[j] = 0u;
+    const unsigned tab_a = smem_u32(s_tab[warp]), flg_a = smem_u32(s_flg[warp]);
+
+#pragma unroll
+    for (int q = 0; q < kRun * G; ++q) tmem_st4(tbase + 4u * (uint32_t)q, p4zero());
+    tmem_wait_st();
+
+    PixelRaw<TIn, TG, G> raw;
+    for (int d0 = 0; d0 < p.D; d0 += ppf) {
+      __syncwarp();
+      fill_run_samples_ho(s_tab[warp], s_flg[warp], p, c, d0, ppf, lane, has_up, has_dn);
+      __syncwarp();
+      const int dend = min(p.D, d0 + ppf);
+      issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp], g_d, ref_row, nsrc, c.c0, C);
+      for (int d = d0; d < dend; ++d) {
+        prefetch_plane(d + kPrefetchPlanes);
+        tmem_wait_st();
+        RunPending<KMAX, G> pend;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          pend.id_top[j] = pend.id_bot[j] = kNoTap;
+#pragma unroll
+          for (int g = 0; g < G; ++g) pend.top[j][g] = pend.bot[j][g] = p4zero();
+        }
+        const int toff = (d - d0) * spp;
+        const WarpSample* tab = s_tab[warp] + toff;
+        const bool more_planes = d + 1 < dend;
+#pragma unroll 1
+        for (int i = 0; i < c.npix; ++i) {
+          const unsigned si = (unsigned)(toff + i * KMAX);
+          const unsigned sa = tab_a + si * 32u;
+          const bool v0 = lds_u32(sa + 16u) != kNoSample;
+          const bool v1 = KMAX == 2 && lds_u32(sa + 32u * (KMAX - 1) + 16u) != kNoSample;
+          const unsigned f0 = lds_u8(flg_a + si);
+          const unsigned f1 = KMAX == 2 ? lds_u8(flg_a + si + (KMAX - 1)) : 0u;
+          const bool in_run = i + 1 < c.npix;
+          const bool has_next = in_run || more_planes;
+          const WarpSample* smp_next = in_run ? tab + (i + 1) * KMAX : tab + spp;
+          const TG* gp_next = in_run ? g_d + (i + 1) * C : g_d + plane_stride;
+          const TIn* rp_next = in_run ? ref_row + (i + 1) * C : ref_row;
+          const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
+          if (v0 && v1)
+            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, true, true>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+          else if (v0)
+            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, true, false>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+          else if (v1)
+            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, false, true>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+          else
+            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, false, false>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          flush_open_p<G, FULL>(ndst[j], pend.id_top[j], pend.top[j], c.c0, C);
+          flush_open_p<G, FULL>(ndst[j], pend.id_bot[j], pend.bot[j], c.c0, C);
+        }
+        g_d += plane_stride;
+      }
+    }
+    tmem_wait_st();
+    float* dst = p.g_feat + ref_off;
+    for (int i = 0; i < c.npix; ++i) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const P4 acc = tmem_ld4(tbase + 4u * (uint32_t)(i * G + g));
+        if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, acc);
+      }
+    }
+  }
+  tmem_free_cta<kCols>(&s_tmem, warp);
+}
+
 // k in {1,2} only (k*kRun <= 32 samples per plane); other k use the pixel kernel.
 template <typename TIn, typename TG>
 static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
@@ -1458,7 +1753,9 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   const bool tm = tuning(4) == 0;          // tuning key 4: 0 = TMEM accumulators (default), 2 = shared memory
   const bool minb3 = tuning(4) != 1;       // tuning key 4: 1 = cap at 128 registers (4 CTAs/SM) instead of 168 (3)
   const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel, 3 = packed
-  const bool lean = tuning(5) == 0 && tuning(4) == 0;   // default: lean packed kernel (sweep_bwd_runq); tuning 5=3: sweep_bwd_runp
+  // default: software-pipelined lean kernel (sweep_bwd_runq2); 5=7: the un-pipelined lean kernel
+  // (sweep_bwd_runq); 5=3: first packed kernel (sweep_bwd_runp)
+  const bool lean = tuning(5) == 0 && tuning(4) == 0;
 #ifdef MVSD_EXP_NORED
   { const int flag = tuning(6); cudaMemcpyToSymbolAsync(c_exp_nored, &flag, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
 #endif
@@ -1467,6 +1764,17 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   do {                                                                                    \
     auto kern = sweep_bwd_runh_kernel<TIn, TG, KM, GG, FU, 3, NS, NVV>;                    \
     constexpr size_t dyn = runh_slot_bytes<KM, GG, NS, NVV>();                            \
+    static bool attr_set = false;                                                         \
+    if (!attr_set) {                                                                      \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);  \
+      attr_set = true;                                                                    \
+    }                                                                                     \
+    kern<<<grid, kRunThreads, dyn, st>>>(p);                                              \
+  } while (0)
+#define MVSD_RUNS(KM, GG, FU, NS)                                                           \
+  do {                                                                                    \
+    auto kern = sweep_bwd_runs_kernel<TIn, TG, KM, GG, FU, 3, NS>;                         \
+    constexpr size_t dyn = runh_slot_bytes<KM, GG, NS, 2>();                              \
     static bool attr_set = false;                                                         \
     if (!attr_set) {                                                                      \
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);  \
@@ -1494,8 +1802,9 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
     else if (tuning(5) == 12) MVSD_RUNF(KM, GG, FU, 4);                                      \
     else if (tuning(5) == 13) MVSD_RUNF(KM, GG, FU, 2, true);                                \
     else if (tuning(5) == 15) MVSD_RUNF(KM, GG, FU, 2, false, true);                         \
-    else if (tuning(5) == 14) sweep_bwd_runq2_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
-    else if (lean) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (tuning(5) == 16) MVSD_RUNS(KM, GG, FU, 2);                                      \
+    else if (lean || tuning(5) == 14) sweep_bwd_runq2_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (tuning(5) == 7) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, false><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4, false><<<grid, kRunThreads, 0, st>>>(p); \
@@ -1515,16 +1824,19 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
 #undef MVSD_RUN
 #undef MVSD_RUNH
 #undef MVSD_RUNF
+#undef MVSD_RUNS
   count_launch();
   return check_launch("plane_sweep_bwd(run)");
 }
 
 int launch_bwd_run(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st) {
+#ifndef MVSD_DEV_FAST      // register-count iterations: compile the headline dtype combination only
   if (feat_dtype == MVSD_F32 && g_dtype == MVSD_F32) return launch_bwd_run_t<float, float>(p, st);
-  if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_F32)
-    return launch_bwd_run_t<__nv_bfloat16, float>(p, st);
   if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_BF16)
     return launch_bwd_run_t<__nv_bfloat16, __nv_bfloat16>(p, st);
+#endif
+  if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_F32)
+    return launch_bwd_run_t<__nv_bfloat16, float>(p, st);
   return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_bwd: dtype combination not built");
 }
 
