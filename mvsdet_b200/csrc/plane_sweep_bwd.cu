@@ -156,14 +156,15 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   p.g_feat = g_feat;
   p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // tuning key 5: 0/unset = software-pipelined lean run-merging kernel (sweep_bwd_runq2, k <= 2),
-  // 7 = the same without the pipelining (sweep_bwd_runq), 1 = pixel kernel, 2 = scalar run-merging
-  // kernel, 3 = first packed run-merging kernel, 4 = block-merging kernel (TMEM + row cache), 5 / 6 =
-  // two- / four-row blocks with two pending columns per source row (plane_sweep_bwd_rows.cu), 8-13 =
-  // row hand-off between the warps of a CTA (sweep_bwd_runh / runf: -25 % RED bytes; 8: 2 stages of
-  // weighted vectors, 9 / 10: 4 / 8 stages of un-weighted vectors, 11 / 12: decisions at table-fill time
-  // with 2 / 4 stages, 13: 11 + L1 prefetch of the next pixel), 15 = 11 + software-pipelined loads.
-  // Every variant is parity-tested (tests/test_gpu_parity.py); measured times in DESIGN.md section 5.
+  // tuning key 5: 0/unset = slim row hand-off between the warps of a CTA with software-pipelined loads
+  // (sweep_bwd_runs, k <= 2: -25 % RED bytes), 14 = pipelined lean kernel without the hand-off
+  // (sweep_bwd_runq2), 7 = un-pipelined lean kernel (sweep_bwd_runq), 1 = pixel kernel, 2 = scalar
+  // run-merging kernel, 3 = first packed run-merging kernel, 4 = block-merging kernel (TMEM + row cache),
+  // 5 / 6 = two- / four-row blocks with two pending columns per source row (plane_sweep_bwd_rows.cu),
+  // 8-13, 15 = earlier hand-off kernels (8: 2 stages of weighted vectors, 9 / 10: 4 / 8 stages of
+  // un-weighted vectors, 11 / 12: decisions at table-fill time with 2 / 4 stages, 13: 11 + L1 prefetch of
+  // the next pixel, 15: 11 + pipelined loads, spills).  Every variant is parity-tested
+  // (tests/test_gpu_parity.py); measured times in DESIGN.md section 5.
   const int variant = tuning(5);
   if ((k == 1 || k == 2) && variant == 4) return launch_bwd_blk(p, feat_dtype, g_dtype, st);
   if ((k == 1 || k == 2) && (variant == 5 || variant == 6))

@@ -809,8 +809,8 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 }
 
 // ---------------------------------------------------------------------------
-// Software-pipelined lean kernel (default since round 1f; tuning key 5 = 7 selects the un-pipelined
-// sweep_bwd_runq above).  ncu's per-warp picture of the lean kernel:
+// Software-pipelined lean kernel (tuning key 5 = 14; 5 = 7 selects the un-pipelined sweep_bwd_runq
+// above).  ncu's per-warp picture of the lean kernel:
 // ~2260 cycles per pixel-plane = one L2 round trip for the 20 loads of the pixel (all issued
 // together, ~1000+ cycles under the RED traffic) followed by ~240 dependent-ish instructions at
 // ~4 cycles each, with only 3 warps per scheduler to overlap the two.  An L1 prefetch of the next
@@ -1446,7 +1446,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runf_kernel(const
 }
 
 // ---------------------------------------------------------------------------
-// Slim hand-off kernel with software-pipelined loads (tuning key 5 = 16).  sweep_bwd_runf with the
+// Slim hand-off kernel with software-pipelined loads (the default since round 1f; also 5 = 16).  sweep_bwd_runf with the
 // pipelining of sweep_bwd_runq2 needs ~190 registers (168 + 80 bytes of spills: slower).  Same
 // algorithm on a register diet: the hand-off queues are addressed with 32-bit shared-space
 // addresses computed from two bases (was six 64-bit pointers), the sample of a pixel is re-read
@@ -1608,8 +1608,10 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
   constexpr int kCols = kRun * G * 4;
   constexpr unsigned kSlot = 2u * G * 512u;
   extern __shared__ __align__(16) unsigned char s_dyn[];          // [kRunRows - 1][KMAX][NSTG] slots
-  __shared__ WarpSample s_tab[kRunRows][32];
-  __shared__ unsigned char s_flg[kRunRows][32];
+  // two table buffers per warp: while the planes of one are processed the other already holds the
+  // next planes, so the load pipeline never drains at a table refill
+  __shared__ WarpSample s_tab[kRunRows][2][32];
+  __shared__ unsigned char s_flg[kRunRows][2][32];
   __shared__ __align__(8) unsigned long long s_bar[kRunRows - 1][KMAX][NSTG][2];   // {full, empty}
   __shared__ uint32_t s_tmem;
   static_assert(sizeof(WarpSample) == 32, "sample table stride");
@@ -1669,19 +1671,22 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
     ho.bar_in = smem_u32(&s_bar[bi][0][0][0]);
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) ho.h_out[j] = ho.h_in[j] = 0u;
-    const unsigned tab_a = smem_u32(s_tab[warp]), flg_a = smem_u32(s_flg[warp]);
+    const unsigned tab_a = smem_u32(s_tab[warp][0]), flg_a = smem_u32(s_flg[warp][0]);
 
 #pragma unroll
     for (int q = 0; q < kRun * G; ++q) tmem_st4(tbase + 4u * (uint32_t)q, p4zero());
     tmem_wait_st();
 
     PixelRaw<TIn, TG, G> raw;
-    for (int d0 = 0; d0 < p.D; d0 += ppf) {
-      __syncwarp();
-      fill_run_samples_ho(s_tab[warp], s_flg[warp], p, c, d0, ppf, lane, has_up, has_dn);
-      __syncwarp();
+    fill_run_samples_ho(s_tab[warp][0], s_flg[warp][0], p, c, 0, ppf, lane, has_up, has_dn);
+    if (ppf < p.D) fill_run_samples_ho(s_tab[warp][1], s_flg[warp][1], p, c, ppf, ppf, lane, has_up, has_dn);
+    __syncwarp();
+    // pipeline prologue: first pixel of the first plane
+    issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp][0], g_d, ref_row, nsrc, c.c0, C);
+    int buf = 0;
+    for (int d0 = 0; d0 < p.D; d0 += ppf, buf ^= 1) {
       const int dend = min(p.D, d0 + ppf);
-      issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp], g_d, ref_row, nsrc, c.c0, C);
+      const bool more_fills = d0 + ppf < p.D;
       for (int d = d0; d < dend; ++d) {
         prefetch_plane(d + kPrefetchPlanes);
         tmem_wait_st();
@@ -1692,9 +1697,12 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
 #pragma unroll
           for (int g = 0; g < G; ++g) pend.top[j][g] = pend.bot[j][g] = p4zero();
         }
-        const int toff = (d - d0) * spp;
-        const WarpSample* tab = s_tab[warp] + toff;
-        const bool more_planes = d + 1 < dend;
+        const int toff = buf * 32 + (d - d0) * spp;
+        const WarpSample* tab = s_tab[warp][0] + toff;
+        const bool last_plane = d + 1 >= dend;
+        const bool more_planes = !last_plane || more_fills;
+        // first sample of the next plane: next rows of this buffer, or the other buffer
+        const WarpSample* tab_next = last_plane ? s_tab[warp][buf ^ 1] : tab + spp;
 #pragma unroll 1
         for (int i = 0; i < c.npix; ++i) {
           const unsigned si = (unsigned)(toff + i * KMAX);
@@ -1705,7 +1713,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
           const unsigned f1 = KMAX == 2 ? lds_u8(flg_a + si + (KMAX - 1)) : 0u;
           const bool in_run = i + 1 < c.npix;
           const bool has_next = in_run || more_planes;
-          const WarpSample* smp_next = in_run ? tab + (i + 1) * KMAX : tab + spp;
+          const WarpSample* smp_next = in_run ? tab + (i + 1) * KMAX : tab_next;
           const TG* gp_next = in_run ? g_d + (i + 1) * C : g_d + plane_stride;
           const TIn* rp_next = in_run ? ref_row + (i + 1) * C : ref_row;
           const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
@@ -1725,6 +1733,11 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
         }
         g_d += plane_stride;
       }
+      // this buffer's planes are done (the loads already in flight read the other buffer): refill it
+      __syncwarp();
+      if (d0 + 2 * ppf < p.D)
+        fill_run_samples_ho(s_tab[warp][buf], s_flg[warp][buf], p, c, d0 + 2 * ppf, ppf, lane, has_up, has_dn);
+      __syncwarp();
     }
     tmem_wait_st();
     float* dst = p.g_feat + ref_off;
@@ -1753,8 +1766,9 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   const bool tm = tuning(4) == 0;          // tuning key 4: 0 = TMEM accumulators (default), 2 = shared memory
   const bool minb3 = tuning(4) != 1;       // tuning key 4: 1 = cap at 128 registers (4 CTAs/SM) instead of 168 (3)
   const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel, 3 = packed
-  // default: software-pipelined lean kernel (sweep_bwd_runq2); 5=7: the un-pipelined lean kernel
-  // (sweep_bwd_runq); 5=3: first packed kernel (sweep_bwd_runp)
+  // default: slim row hand-off with software-pipelined loads (sweep_bwd_runs); 5=14: pipelined lean
+  // kernel without the hand-off (sweep_bwd_runq2); 5=7: un-pipelined lean kernel (sweep_bwd_runq);
+  // 5=3: first packed kernel (sweep_bwd_runp)
   const bool lean = tuning(5) == 0 && tuning(4) == 0;
 #ifdef MVSD_EXP_NORED
   { const int flag = tuning(6); cudaMemcpyToSymbolAsync(c_exp_nored, &flag, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
@@ -1802,8 +1816,8 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
     else if (tuning(5) == 12) MVSD_RUNF(KM, GG, FU, 4);                                      \
     else if (tuning(5) == 13) MVSD_RUNF(KM, GG, FU, 2, true);                                \
     else if (tuning(5) == 15) MVSD_RUNF(KM, GG, FU, 2, false, true);                         \
-    else if (tuning(5) == 16) MVSD_RUNS(KM, GG, FU, 2);                                      \
-    else if (lean || tuning(5) == 14) sweep_bwd_runq2_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (lean || tuning(5) == 16) MVSD_RUNS(KM, GG, FU, 2);                              \
+    else if (tuning(5) == 14) sweep_bwd_runq2_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (tuning(5) == 7) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, false><<<grid, kRunThreads, 0, st>>>(p); \
