@@ -325,12 +325,16 @@ def run_own_arm(args, cfg, cfg_json):
             roofline["traffic"] = tj.get(top)
             red = tj.get(top + "_red_payload")
             if red:
-                # what actually limits the scatter kernel: fp32 REDs into L2.  Ceiling measured by
+                # the scatter kernel's second stream: fp32 REDs into L2.  Ceiling measured by
                 # tools/microbench_red.cu on this pool's B200 (profiles/r01_b_microbench_red.txt).
+                # Up to round 1e this stream (3.6 GB at > 80 % of the ceiling) was the limiter; with
+                # the row hand-off it is 2.7 GB and the kernel is bound by instructions per pixel at
+                # 12 warps/SM (issue-active 49 %) -- reported for that reason.
                 red_gbs = red / (kernels[top]["ms"] * 1e-3) / 1e9
                 roofline["limiter"] = {"what": "fp32 red.global.add.v4 payload into L2 (ncu l1tex2xbar write bytes)",
                                        "red_payload_bytes": red, "achieved_gbs": round(red_gbs, 1),
-                                       "ceiling_gbs": 5700.0, "frac": round(red_gbs / 5700.0, 3)}
+                                       "ceiling_gbs": 5700.0, "frac": round(red_gbs / 5700.0, 3),
+                                       "binding": red_gbs / 5700.0 > 0.8}
         except Exception:
             pass
 
