@@ -161,10 +161,10 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   // (sweep_bwd_runq2), 7 = un-pipelined lean kernel (sweep_bwd_runq), 1 = pixel kernel, 2 = scalar
   // run-merging kernel, 3 = first packed run-merging kernel, 4 = block-merging kernel (TMEM + row cache),
   // 5 / 6 = two- / four-row blocks with two pending columns per source row (plane_sweep_bwd_rows.cu),
-  // 8-13, 15 = earlier hand-off kernels (8: 2 stages of weighted vectors, 9 / 10: 4 / 8 stages of
-  // un-weighted vectors, 11 / 12: decisions at table-fill time with 2 / 4 stages, 13: 11 + L1 prefetch of
-  // the next pixel, 15: 11 + pipelined loads, spills).  Every variant is parity-tested
-  // (tests/test_gpu_parity.py); measured times in DESIGN.md section 5.
+  // 8 / 11 = earlier hand-off kernels (8: decisions per pixel from the neighbouring rows' tables, CTA
+  // barrier per refill; 11: decisions at table-fill time, un-pipelined).  Every variant is parity-tested
+  // (tests/test_gpu_parity.py); measured times, and the variants that were measured and removed
+  // (deeper queues, L1 prefetch of the next pixel), in DESIGN.md section 5.
   const int variant = tuning(5);
   if ((k == 1 || k == 2) && variant == 4) return launch_bwd_blk(p, feat_dtype, g_dtype, st);
   if ((k == 1 || k == 2) && (variant == 5 || variant == 6))

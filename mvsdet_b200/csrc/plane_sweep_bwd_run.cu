@@ -818,7 +818,8 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 // the loads of the NEXT pixel are issued into the raw-load registers as soon as the blend has
 // consumed the current ones, i.e. before the variance algebra, the tensor-memory update and the
 // scatter: the same registers, no extra L1 traffic, and the round trip overlaps ~60 % of the
-// pixel's instructions.  The pipeline runs across the planes of one sample-table fill.
+// pixel's instructions.  The pipeline runs across the planes of one sample-table fill.  (With the
+// un-slimmed hand-off kernel the same pipelining needed 168 registers + 80 bytes of spills: slower.)
 // ---------------------------------------------------------------------------
 template <typename TIn, typename TG, int G>
 struct PixelRaw {
@@ -849,14 +850,13 @@ __device__ __forceinline__ void issue_pixel_loads(PixelRaw<TIn, TG, G>& raw, con
   }
 }
 
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1, bool HO = false,
-          typename HOC = HandoffCtx<KMAX, G>>
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool V0, bool V1>
 __device__ __forceinline__ void pixel_q2(RunPending<KMAX, G>& pend, PixelRaw<TIn, TG, G>& raw,
                                          const WarpSample& s0, const WarpSample& s1, bool has_next,
                                          const WarpSample* smp_next, const TG* __restrict__ gp_next,
                                          const TIn* __restrict__ rp_next, const TIn* const (&nsrc)[KMAX],
                                          float* const (&ndst)[KMAX], uint32_t taddr, u64 inv_n2,
-                                         u64 two_inv_n2, int c0, int C, HOC* ho = nullptr) {
+                                         u64 two_inv_n2, int c0, int C) {
   P4 w0[G], w1[G], gw0[G], gw1[G], ref[G], gv[G];
   if (V0) blend_taps<TIn, G>(raw.t0, s0, w0);
   if (V1) blend_taps<TIn, G>(raw.t1, s1, w1);
@@ -879,27 +879,13 @@ __device__ __forceinline__ void pixel_q2(RunPending<KMAX, G>& pend, PixelRaw<TIn
     if (V1) gw1[g] = p4mul(gv[g], p4sub(w1[g], mu));
   }
   if (V0) {
-    if (HO) {
-      scatter_h<G, FULL, HOC::kStages, HOC::kVec>(ndst[0], gw0, s0, pend.id_top[0], pend.top[0], pend.id_bot[0], pend.bot[0],
-                         ho->send[0], ho->out_slot[0], ho->out_full[0], ho->out_empty[0], ho->h_out[0],
-                         ho->recv[0], ho->up_w10[0], ho->up_w11[0], ho->in_slot[0], ho->in_full[0],
-                         ho->in_empty[0], ho->h_in[0], ho->lane, c0, C);
-    } else {
-      side_q<G, FULL>(ndst[0], gw0, s0.w00, s0.w01, s0.p00, s0.p01, pend.id_top[0], pend.top[0], c0, C);
-      side_q<G, FULL>(ndst[0], gw0, s0.w10, s0.w11, s0.p10, s0.p11, pend.id_bot[0], pend.bot[0], c0, C);
-    }
+    side_q<G, FULL>(ndst[0], gw0, s0.w00, s0.w01, s0.p00, s0.p01, pend.id_top[0], pend.top[0], c0, C);
+    side_q<G, FULL>(ndst[0], gw0, s0.w10, s0.w11, s0.p10, s0.p11, pend.id_bot[0], pend.bot[0], c0, C);
   }
   if (V1) {
     constexpr int J = KMAX - 1;
-    if (HO) {
-      scatter_h<G, FULL, HOC::kStages, HOC::kVec>(ndst[J], gw1, s1, pend.id_top[J], pend.top[J], pend.id_bot[J], pend.bot[J],
-                         ho->send[J], ho->out_slot[J], ho->out_full[J], ho->out_empty[J], ho->h_out[J],
-                         ho->recv[J], ho->up_w10[J], ho->up_w11[J], ho->in_slot[J], ho->in_full[J],
-                         ho->in_empty[J], ho->h_in[J], ho->lane, c0, C);
-    } else {
-      side_q<G, FULL>(ndst[J], gw1, s1.w00, s1.w01, s1.p00, s1.p01, pend.id_top[J], pend.top[J], c0, C);
-      side_q<G, FULL>(ndst[J], gw1, s1.w10, s1.w11, s1.p10, s1.p11, pend.id_bot[J], pend.bot[J], c0, C);
-    }
+    side_q<G, FULL>(ndst[J], gw1, s1.w00, s1.w01, s1.p00, s1.p01, pend.id_top[J], pend.top[J], c0, C);
+    side_q<G, FULL>(ndst[J], gw1, s1.w10, s1.w11, s1.p10, s1.p11, pend.id_bot[J], pend.bot[J], c0, C);
   }
 }
 
@@ -1033,9 +1019,9 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq2_kernel(cons
 template <int KMAX, int G, int NSTG, int NV>
 constexpr size_t runh_slot_bytes() { return sizeof(HandoffSlot<G, NV>) * (kRunRows - 1) * KMAX * NSTG; }
 
-// NSTG stages of NV vectors per (row boundary, neighbour): <2, 2> is the first version (tuning 5 = 8),
-// <4, 1> (5 = 9) and <8, 1> (5 = 10) the deeper queues of un-weighted contributions.  The slots live in
-// dynamic shared memory (48 KB for <8, 1> with G = 2, k = 2).
+// NSTG stages of NV vectors per (row boundary, neighbour): <2, 2> is what is built (tuning 5 = 8).  Deeper
+// queues of un-weighted contributions (<4, 1>, <8, 1>) were measured in round 1f: 0.862 ms against 0.889 ms,
+// no difference between 4 and 8 stages.  The slots live in dynamic shared memory.
 template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, int NSTG = 2, int NV = 2>
 __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const SweepParams p) {
   constexpr int kCols = kRun * G * 4;
@@ -1197,8 +1183,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runh_kernel(const
 }
 
 // ---------------------------------------------------------------------------
-// Row hand-off with the decisions taken at table-fill time (tuning key 5 = 11: 2 stages,
-// 12: 4 stages).  ncu on sweep_bwd_runh: 366 M warp instructions against 274 M for the lean
+// Row hand-off with the decisions taken at table-fill time (tuning key 5 = 11).  ncu on sweep_bwd_runh: 366 M warp instructions against 274 M for the lean
 // kernel and a CTA barrier every two planes -- the per-pixel send / receive tests read the
 // sample tables of the rows above and below (six extra 16-byte shared loads and ~30 ALU
 // instructions per pixel), which is also what forces the four warps to refill their tables
@@ -1250,37 +1235,8 @@ __device__ __forceinline__ void fill_run_samples_ho(WarpSample* tab, unsigned ch
   }
 }
 
-// L1 prefetch of everything the NEXT pixel of the run will load (taps of both neighbours, upstream
-// gradient, reference feature): one 128-byte line per lane.  The hand-off kernel is not bound by
-// the RED stream any more (2.7 GB at 3.4 TB/s) but by the serial chain "wait for one L2 round trip,
-// then ~300 instructions" of each of its 12 warps per SM; with the lines already in L1 the round
-// trip of the next pixel overlaps this pixel's arithmetic and scatter.  FULL slices only (every
-// line of the slice is inside the tensor).
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-}
-
-template <typename TIn, typename TG, int KMAX, int G>
-__device__ __forceinline__ void prefetch_pixel_l1(const WarpSample* smp, const TIn* const (&nsrc)[KMAX],
-                                                  const TG* gp, const TIn* rp, int lane) {
-  constexpr int kTapLineElems = 128 / (int)sizeof(TIn);
-  constexpr int kTapLines = (128 * G) / kTapLineElems;          // lines per tap of this warp's slice
-  constexpr int kGLineElems = 128 / (int)sizeof(TG);
-  constexpr int kGLines = (128 * G) / kGLineElems;
-  const int j = lane >> 4, tap = (lane >> 2) & 3, l = lane & 3;
-  if (j < KMAX && l < kTapLines) {
-    const unsigned off = reinterpret_cast<const unsigned*>(smp + j)[4 + tap];
-    if (off != kNoSample)
-      prefetch_l1(at(j == 0 ? nsrc[0] : nsrc[KMAX - 1], off) + (kTapLineElems * l - 4 * lane));
-  }
-  // lanes [0, kGLines): gradient lines; the next kTapLines lanes: reference-feature lines
-  if (lane < kGLines) prefetch_l1(gp + (kGLineElems * lane - 4 * lane));
-  else if (lane < kGLines + kTapLines) prefetch_l1(rp + (kTapLineElems * (lane - kGLines) - 4 * lane));
-}
-
 // requires p.k == KMAX
-// SP = true: software-pipelined loads as in sweep_bwd_runq2 (tuning key 5 = 15).
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, int NSTG, bool PF = false, bool SP = false>
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, int NSTG>
 __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runf_kernel(const SweepParams p) {
   constexpr int kCols = kRun * G * 4;
   constexpr int NV = 2;
@@ -1354,13 +1310,11 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runf_kernel(const
     for (int q = 0; q < kRun * G; ++q) tmem_st4(tbase + 4u * (uint32_t)q, p4zero());
     tmem_wait_st();
 
-    PixelRaw<TIn, TG, G> raw;
     for (int d0 = 0; d0 < p.D; d0 += ppf) {
       __syncwarp();
       fill_run_samples_ho(s_tab[warp], s_flg[warp], p, c, d0, ppf, lane, has_up, has_dn);
       __syncwarp();
       const int dend = min(p.D, d0 + ppf);
-      if (SP) issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp], g_d, ref_row, nsrc, c.c0, C);
       for (int d = d0; d < dend; ++d) {
         prefetch_plane(d + kPrefetchPlanes);
         tmem_wait_st();
@@ -1376,13 +1330,6 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runf_kernel(const
         const unsigned char* flg = s_flg[warp] + toff;
 #pragma unroll 1
         for (int i = 0; i < c.npix; ++i) {
-          if (PF && FULL) {
-            if (i + 1 < c.npix)
-              prefetch_pixel_l1<TIn, TG, KMAX, G>(tab + (i + 1) * KMAX, nsrc, g_d + (i + 1) * C,
-                                                  ref_row + (i + 1) * C, lane);
-            else if (d + 1 < dend)          // first pixel of the next plane (its table is already filled)
-              prefetch_pixel_l1<TIn, TG, KMAX, G>(tab + spp, nsrc, g_d + plane_stride, ref_row, lane);
-          }
           const WarpSample s0 = tab[i * KMAX];
           const WarpSample s1 = tab[i * KMAX + (KMAX - 1)];
           const bool v0 = s0.p00 != kNoSample;
@@ -1399,22 +1346,6 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runf_kernel(const
           const TG* gp = g_d + i * C;
           const TIn* rp = ref_row + i * C;
           const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
-          if (SP) {
-            const bool in_run = i + 1 < c.npix;
-            const bool has_next = in_run || d + 1 < dend;
-            const WarpSample* smp_next = in_run ? tab + (i + 1) * KMAX : tab + spp;
-            const TG* gp_next = in_run ? gp + C : g_d + plane_stride;
-            const TIn* rp_next = in_run ? rp + C : ref_row;
-            if (v0 && v1)
-              pixel_q2<TIn, TG, KMAX, G, FULL, true, true, true, HOC>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
-            else if (v0)
-              pixel_q2<TIn, TG, KMAX, G, FULL, true, false, true, HOC>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
-            else if (v1)
-              pixel_q2<TIn, TG, KMAX, G, FULL, false, true, true, HOC>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
-            else
-              pixel_q2<TIn, TG, KMAX, G, FULL, false, false, true, HOC>(pend, raw, s0, s1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
-            continue;
-          }
           if (v0 && v1)
             pixel_q<TIn, TG, KMAX, G, FULL, true, true, true, HOC>(pend, s0, s1, gp, rp, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, &ho);
           else if (v0)
@@ -1796,9 +1727,9 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
     }                                                                                     \
     kern<<<grid, kRunThreads, dyn, st>>>(p);                                              \
   } while (0)
-#define MVSD_RUNF(KM, GG, FU, NS, ...)                                                      \
+#define MVSD_RUNF(KM, GG, FU, NS)                                                           \
   do {                                                                                    \
-    auto kern = sweep_bwd_runf_kernel<TIn, TG, KM, GG, FU, 3, NS, ##__VA_ARGS__>;          \
+    auto kern = sweep_bwd_runf_kernel<TIn, TG, KM, GG, FU, 3, NS>;                         \
     constexpr size_t dyn = runh_slot_bytes<KM, GG, NS, 2>();                              \
     static bool attr_set = false;                                                         \
     if (!attr_set) {                                                                      \
@@ -1810,12 +1741,7 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
 #define MVSD_RUN(KM, GG, FU)                                                              \
   do {                                                                                    \
     if (tuning(5) == 8) MVSD_RUNH(KM, GG, FU, 2, 2);                                         \
-    else if (tuning(5) == 9) MVSD_RUNH(KM, GG, FU, 4, 1);                                    \
-    else if (tuning(5) == 10) MVSD_RUNH(KM, GG, FU, 8, 1);                                   \
     else if (tuning(5) == 11) MVSD_RUNF(KM, GG, FU, 2);                                      \
-    else if (tuning(5) == 12) MVSD_RUNF(KM, GG, FU, 4);                                      \
-    else if (tuning(5) == 13) MVSD_RUNF(KM, GG, FU, 2, true);                                \
-    else if (tuning(5) == 15) MVSD_RUNF(KM, GG, FU, 2, false, true);                         \
     else if (lean || tuning(5) == 16) MVSD_RUNS(KM, GG, FU, 2);                              \
     else if (tuning(5) == 14) sweep_bwd_runq2_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (tuning(5) == 7) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \

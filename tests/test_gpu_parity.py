@@ -240,14 +240,13 @@ def test_single_view_scene_variance_is_zero():
     assert float(var.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 11, 14])
 @pytest.mark.parametrize("case", ["scannet_tiny", "two_views", "wide_c"])
 def test_plane_sweep_bwd_variants(case, variant):
     """Every opt-in plane-sweep backward (mvsd_set_tuning key 5: 1 pixel kernel,
     2 scalar run kernel, 3 first packed run kernel, 4 block-merging, 5/6 two-/four-row blocks with two
-    pending columns, 7 lean run kernel, 8-13 and 15 the row hand-off kernels before the default one
-    (shared-memory slots + mbarriers; queue depth, decisions at fill time, L1 prefetch, pipelined loads),
-    14 pipelined lean kernel) must give the reference gradient, like the default (slim hand-off with
+    pending columns, 7 lean run kernel, 8 / 11 the row hand-off kernels before the default one
+    (shared-memory slots + mbarriers; decisions per pixel / at fill time), 14 pipelined lean kernel) must give the reference gradient, like the default (slim hand-off with
     pipelined loads)."""
     from mvsdet_b200 import _lib
     scene, gold = load_golden(case)
@@ -261,7 +260,7 @@ def test_plane_sweep_bwd_variants(case, variant):
 
 
 @pytest.mark.parametrize("hw", [(13, 21), (9, 7), (17, 40)])
-@pytest.mark.parametrize("variant", [0, 5, 7, 8, 11, 14, 15])
+@pytest.mark.parametrize("variant", [0, 5, 7, 8, 11, 14])
 def test_ragged_feature_map_sizes(hw, variant):
     """Feature maps whose height is not a multiple of the CTA's 4 rows and whose width is
     not a multiple of the 8-pixel run (partial runs, idle warps, hand-off with a missing
