@@ -1683,6 +1683,356 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
   tmem_free_cta<kCols>(&s_tmem, warp);
 }
 
+#ifdef MVSD_EXP_TMEM_PENDING
+// ---------------------------------------------------------------------------
+// EXPERIMENT, NOT BUILT BY DEFAULT AND NOT YET RUN ON A GPU: the slim
+// hand-off kernel with the pending taps in tensor memory instead of 32 registers, compiled for four
+// CTAs per SM (128 registers).  Written at the end of round 1 to answer the register question with
+// ptxas; correctness and speed are the first measurement of round 2
+// (build with MVSD_EXTRA_NVCC_FLAGS=-DMVSD_EXP_TMEM_PENDING, select with tuning key 5 = 17).
+// TMEM columns per CTA: [0, 64) reference gradients, [64, 96) pending taps
+// ((neighbour * 2 + side) * G + group) * 4; allocation 128 columns, 4 CTAs = the whole TMEM.
+// ---------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void tm_ldv(uint32_t ta, P4 (&v)[G]) {
+  float f[G][4];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(f[g][0]), "=f"(f[g][1]), "=f"(f[g][2]), "=f"(f[g][3]) : "r"(ta + 4u * (uint32_t)g) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int g = 0; g < G; ++g) v[g] = P4{pk2(f[g][0], f[g][1]), pk2(f[g][2], f[g][3])};
+}
+template <int G>
+__device__ __forceinline__ void tm_stv(uint32_t ta, const P4 (&v)[G]) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) tmem_st4(ta + 4u * (uint32_t)g, v[g]);
+}
+
+// side_q with the pending accumulator of this (neighbour, side) at TMEM address ta
+template <int G, bool FULL>
+__device__ __forceinline__ void side_qt(float* dst, const P4 (&gw)[G], float w_left, float w_right,
+                                        unsigned p_left, unsigned p_right, unsigned& open_id, uint32_t ta,
+                                        int c0, int C) {
+  const u64 wl = pk2(w_left, w_left), wr = pk2(w_right, w_right);
+  P4 a[G], o[G];
+  tmem_wait_st();                          // the previous pixel's store to these columns
+  if (open_id == p_left) {
+    tm_ldv<G>(ta, o);
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = p4fma(gw[g], wl, o[g]);
+    red_group_p<G, FULL>(dst, p_left, a, c0, C);
+#pragma unroll
+    for (int g = 0; g < G; ++g) o[g] = p4scale(gw[g], wr);
+    tm_stv<G>(ta, o);
+    open_id = w_right != 0.f ? p_right : kNoTap;
+  } else if (open_id == p_right && w_right != 0.f) {
+    tm_ldv<G>(ta, o);
+#pragma unroll
+    for (int g = 0; g < G; ++g) o[g] = p4fma(gw[g], wr, o[g]);
+    tm_stv<G>(ta, o);
+    if (w_left != 0.f) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) a[g] = p4scale(gw[g], wl);
+      red_group_p<G, FULL>(dst, p_left, a, c0, C);
+    }
+  } else {
+    if (open_id != kNoTap) {
+      tm_ldv<G>(ta, o);
+      red_group_p<G, FULL>(dst, open_id, o, c0, C);
+    }
+    if (w_left != 0.f) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) a[g] = p4scale(gw[g], wl);
+      red_group_p<G, FULL>(dst, p_left, a, c0, C);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) o[g] = p4scale(gw[g], wr);
+    tm_stv<G>(ta, o);
+    open_id = w_right != 0.f ? p_right : kNoTap;
+  }
+}
+
+// side_c (pre-weighted left / right contributions) with the pending accumulator in TMEM
+template <int G, bool FULL>
+__device__ __forceinline__ void side_ct(float* dst, const P4 (&cl)[G], const P4 (&cr)[G], bool nz_left,
+                                        bool nz_right, unsigned p_left, unsigned p_right, unsigned& open_id,
+                                        uint32_t ta, int c0, int C) {
+  P4 a[G], o[G];
+  tmem_wait_st();
+  if (open_id == p_left) {
+    tm_ldv<G>(ta, o);
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = p4add(cl[g], o[g]);
+    red_group_p<G, FULL>(dst, p_left, a, c0, C);
+    tm_stv<G>(ta, cr);
+    open_id = nz_right ? p_right : kNoTap;
+  } else if (open_id == p_right && nz_right) {
+    tm_ldv<G>(ta, o);
+#pragma unroll
+    for (int g = 0; g < G; ++g) o[g] = p4add(cr[g], o[g]);
+    tm_stv<G>(ta, o);
+    if (nz_left) red_group_p<G, FULL>(dst, p_left, cl, c0, C);
+  } else {
+    if (open_id != kNoTap) {
+      tm_ldv<G>(ta, o);
+      red_group_p<G, FULL>(dst, open_id, o, c0, C);
+    }
+    if (nz_left) red_group_p<G, FULL>(dst, p_left, cl, c0, C);
+    tm_stv<G>(ta, cr);
+    open_id = nz_right ? p_right : kNoTap;
+  }
+}
+
+template <int G, bool FULL>
+__device__ __forceinline__ void flush_open_t(float* dst, unsigned& id, uint32_t ta, int c0, int C) {
+  if (id != kNoTap) {
+    P4 o[G];
+    tmem_wait_st();
+    tm_ldv<G>(ta, o);
+    red_group_p<G, FULL>(dst, id, o, c0, C);
+  }
+  id = kNoTap;
+}
+
+template <int KMAX>
+struct PendingIds {
+  unsigned top[KMAX], bot[KMAX];
+};
+
+template <int G, bool FULL, int NSTG, int J, int KMAX>
+__device__ __forceinline__ void scatter_ht(float* dst, const P4 (&gw)[G], float4 wq, uint4 oq,
+                                           unsigned& id_top, unsigned& id_bot, uint32_t ta_top, uint32_t ta_bot,
+                                           unsigned flags, HoLite<KMAX>& ho, int c0, int C) {
+  constexpr unsigned kVec = 512u;
+  constexpr unsigned kSlot = 2u * G * kVec;
+  constexpr unsigned jslot = (unsigned)J * NSTG * kSlot, jbar = (unsigned)J * NSTG * 16u;
+  if (flags & kHoSend) {
+    const unsigned h = ho.h_out[J]++;
+    const unsigned stg = h & (unsigned)(NSTG - 1), ph = (h / (unsigned)NSTG) & 1u;
+    const unsigned bar = ho.bar_out + jbar + stg * 16u;
+    mbar_wait_a(bar + 8u, ph ^ 1u);
+    const unsigned a = ho.slot_out + jslot + stg * kSlot;
+    const u64 w10 = pk2(wq.z, wq.z), w11 = pk2(wq.w, wq.w);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      sts_p4(a + (unsigned)g * kVec, p4scale(gw[g], w10));
+      sts_p4(a + (unsigned)(G + g) * kVec, p4scale(gw[g], w11));
+    }
+    mbar_arrive_a(bar);
+  } else {
+    side_qt<G, FULL>(dst, gw, wq.z, wq.w, oq.z, oq.w, id_bot, ta_bot, c0, C);
+  }
+  if (flags & kHoRecv) {
+    const unsigned h = ho.h_in[J]++;
+    const unsigned stg = h & (unsigned)(NSTG - 1), ph = (h / (unsigned)NSTG) & 1u;
+    const unsigned bar = ho.bar_in + jbar + stg * 16u;
+    mbar_wait_a(bar, ph);
+    const unsigned a = ho.slot_in + jslot + stg * kSlot;
+    P4 cl[G], cr[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cl[g] = lds_p4(a + (unsigned)g * kVec);
+      cr[g] = lds_p4(a + (unsigned)(G + g) * kVec);
+    }
+    mbar_arrive_a(bar + 8u);
+    const u64 w00 = pk2(wq.x, wq.x), w01 = pk2(wq.y, wq.y);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cl[g] = p4fma(gw[g], w00, cl[g]);
+      cr[g] = p4fma(gw[g], w01, cr[g]);
+    }
+    side_ct<G, FULL>(dst, cl, cr, (flags & kHoNzLeft) != 0u, (flags & kHoNzRight) != 0u, oq.x, oq.y, id_top,
+                     ta_top, c0, C);
+  } else {
+    side_qt<G, FULL>(dst, gw, wq.x, wq.y, oq.x, oq.y, id_top, ta_top, c0, C);
+  }
+}
+
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int NSTG, bool V0, bool V1>
+__device__ __forceinline__ void pixel_q4(PendingIds<KMAX>& ids, uint32_t tpend, PixelRaw<TIn, TG, G>& raw,
+                                         unsigned sa, unsigned flags0, unsigned flags1, bool has_next,
+                                         const WarpSample* smp_next, const TG* __restrict__ gp_next,
+                                         const TIn* __restrict__ rp_next, const TIn* const (&nsrc)[KMAX],
+                                         float* const (&ndst)[KMAX], uint32_t taddr, u64 inv_n2,
+                                         u64 two_inv_n2, int c0, int C, HoLite<KMAX>& ho) {
+  constexpr unsigned kS1 = 32u * (KMAX - 1);
+  constexpr uint32_t kSide = 4u * G;                  // TMEM columns of one pending accumulator
+  P4 w0[G], w1[G], gw0[G], gw1[G], ref[G], gv[G];
+  if (V0) blend_taps_w<TIn, G>(raw.t0, lds_f4(sa), w0);
+  if (V1) blend_taps_w<TIn, G>(raw.t1, lds_f4(sa + kS1), w1);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    ref[g] = p4from(raw.r[g]);
+    gv[g] = p4scale(p4from(raw.g[g]), two_inv_n2);
+  }
+  if (has_next) issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, smp_next, gp_next, rp_next, nsrc, c0, C);
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    P4 mu = ref[g];
+    if (V0) mu = p4add(mu, w0[g]);
+    if (V1) mu = p4add(mu, w1[g]);
+    mu = p4scale(mu, inv_n2);
+    const uint32_t ta = taddr + 4u * (uint32_t)g;
+    tmem_st4(ta, p4fma(gv[g], p4sub(ref[g], mu), tmem_ld4(ta)));
+    if (V0) gw0[g] = p4mul(gv[g], p4sub(w0[g], mu));
+    if (V1) gw1[g] = p4mul(gv[g], p4sub(w1[g], mu));
+  }
+  if (V0)
+    scatter_ht<G, FULL, NSTG, 0, KMAX>(ndst[0], gw0, lds_f4(sa), lds_u4(sa + 16u), ids.top[0], ids.bot[0],
+                                       tpend, tpend + kSide, flags0, ho, c0, C);
+  if (V1)
+    scatter_ht<G, FULL, NSTG, KMAX - 1, KMAX>(ndst[KMAX - 1], gw1, lds_f4(sa + kS1), lds_u4(sa + kS1 + 16u),
+                                              ids.top[KMAX - 1], ids.bot[KMAX - 1],
+                                              tpend + 2u * kSide * (KMAX - 1), tpend + 2u * kSide * (KMAX - 1) + kSide,
+                                              flags1, ho, c0, C);
+}
+
+// requires p.k == KMAX
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int NSTG>
+__global__ void __launch_bounds__(kRunThreads, 4) sweep_bwd_runt_kernel(const SweepParams p) {
+  constexpr int kRefCols = kRun * G * 4;                       // 64
+  constexpr int kCols = 128;                                   // 64 + 2 * KMAX * G * 4 <= 96 -> 128
+  static_assert(kRefCols + 2 * KMAX * G * 4 <= kCols, "TMEM budget");
+  constexpr unsigned kSlot = 2u * G * 512u;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ WarpSample s_tab[kRunRows][2][32];
+  __shared__ unsigned char s_flg[kRunRows][2][32];
+  __shared__ __align__(8) unsigned long long s_bar[kRunRows - 1][KMAX][NSTG][2];
+  __shared__ uint32_t s_tmem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RunCoord c = run_coord<G>(p, warp, lane);
+  if (threadIdx.x < (kRunRows - 1) * KMAX * NSTG * 2) {
+    mbar_init(&s_bar[0][0][0][0] + threadIdx.x, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);
+  const uint32_t tpend = tbase + (uint32_t)kRefCols;
+  if (c.y < p.H) {
+    const int C = p.C, HW = p.H * p.W;
+    const TIn* feat = static_cast<const TIn*>(p.feat);
+    const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const TIn* ref_row = feat + ref_off;
+    const size_t plane_stride = (size_t)HW * C;
+    const TG* g_d = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    const bool one_chunk = p.slices == 1;
+    const unsigned pf_bytes = (unsigned)((one_chunk ? (size_t)c.npix * C : (size_t)min(128 * G, C - (c.c0 - 4 * lane))) *
+                                         sizeof(TG)) & ~15u;
+    const TG* pf_base = g_d - 4 * lane;
+    const bool pf_ok = pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
+                       ((plane_stride * sizeof(TG)) & 15) == 0;
+    auto prefetch_plane = [&](int d) {
+      if (!pf_ok || d >= p.D) return;
+      const TG* q = pf_base + (size_t)d * plane_stride;
+      if (one_chunk) {
+        if (lane == 0) prefetch_l2(q, pf_bytes);
+      } else if (lane < c.npix) {
+        prefetch_l2(q + (size_t)lane * C, pf_bytes);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < kPrefetchPlanes; ++d) prefetch_plane(d);
+
+    const TIn* nsrc[KMAX];
+    float* ndst[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+    }
+    const float inv_n = 1.0f / (float)(KMAX + 1);
+    const u64 inv_n2 = pk2(inv_n, inv_n);
+    const u64 two_inv_n2 = pk2(2.0f * inv_n, 2.0f * inv_n);
+    constexpr int spp = kRun * KMAX;
+    constexpr int ppf = 32 / spp > 0 ? 32 / spp : 1;
+    const bool has_up = warp > 0;
+    const bool has_dn = warp + 1 < kRunRows && c.y + 1 < p.H;
+    const int bo = min(warp, kRunRows - 2), bi = max(warp - 1, 0);
+    HoLite<KMAX> ho;
+    ho.slot_out = smem_u32(s_dyn) + (unsigned)(bo * KMAX * NSTG) * kSlot + (unsigned)lane * 16u;
+    ho.slot_in = smem_u32(s_dyn) + (unsigned)(bi * KMAX * NSTG) * kSlot + (unsigned)lane * 16u;
+    ho.bar_out = smem_u32(&s_bar[bo][0][0][0]);
+    ho.bar_in = smem_u32(&s_bar[bi][0][0][0]);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) ho.h_out[j] = ho.h_in[j] = 0u;
+    const unsigned tab_a = smem_u32(s_tab[warp][0]), flg_a = smem_u32(s_flg[warp][0]);
+
+#pragma unroll
+    for (int q = 0; q < kRun * G; ++q) tmem_st4(tbase + 4u * (uint32_t)q, p4zero());
+    tmem_wait_st();
+
+    PixelRaw<TIn, TG, G> raw;
+    fill_run_samples_ho(s_tab[warp][0], s_flg[warp][0], p, c, 0, ppf, lane, has_up, has_dn);
+    if (ppf < p.D) fill_run_samples_ho(s_tab[warp][1], s_flg[warp][1], p, c, ppf, ppf, lane, has_up, has_dn);
+    __syncwarp();
+    issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp][0], g_d, ref_row, nsrc, c.c0, C);
+    int buf = 0;
+    for (int d0 = 0; d0 < p.D; d0 += ppf, buf ^= 1) {
+      const int dend = min(p.D, d0 + ppf);
+      const bool more_fills = d0 + ppf < p.D;
+      for (int d = d0; d < dend; ++d) {
+        prefetch_plane(d + kPrefetchPlanes);
+        tmem_wait_st();
+        PendingIds<KMAX> ids;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) ids.top[j] = ids.bot[j] = kNoTap;
+        const int toff = buf * 32 + (d - d0) * spp;
+        const WarpSample* tab = s_tab[warp][0] + toff;
+        const bool last_plane = d + 1 >= dend;
+        const bool more_planes = !last_plane || more_fills;
+        const WarpSample* tab_next = last_plane ? s_tab[warp][buf ^ 1] : tab + spp;
+#pragma unroll 1
+        for (int i = 0; i < c.npix; ++i) {
+          const unsigned si = (unsigned)(toff + i * KMAX);
+          const unsigned sa = tab_a + si * 32u;
+          const bool v0 = lds_u32(sa + 16u) != kNoSample;
+          const bool v1 = KMAX == 2 && lds_u32(sa + 32u * (KMAX - 1) + 16u) != kNoSample;
+          const unsigned f0 = lds_u8(flg_a + si);
+          const unsigned f1 = KMAX == 2 ? lds_u8(flg_a + si + (KMAX - 1)) : 0u;
+          const bool in_run = i + 1 < c.npix;
+          const bool has_next = in_run || more_planes;
+          const WarpSample* smp_next = in_run ? tab + (i + 1) * KMAX : tab_next;
+          const TG* gp_next = in_run ? g_d + (i + 1) * C : g_d + plane_stride;
+          const TIn* rp_next = in_run ? ref_row + (i + 1) * C : ref_row;
+          const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
+          if (v0 && v1)
+            pixel_q4<TIn, TG, KMAX, G, FULL, NSTG, true, true>(ids, tpend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+          else if (v0)
+            pixel_q4<TIn, TG, KMAX, G, FULL, NSTG, true, false>(ids, tpend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+          else if (v1)
+            pixel_q4<TIn, TG, KMAX, G, FULL, NSTG, false, true>(ids, tpend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+          else
+            pixel_q4<TIn, TG, KMAX, G, FULL, NSTG, false, false>(ids, tpend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          flush_open_t<G, FULL>(ndst[j], ids.top[j], tpend + 8u * G * (uint32_t)j, c.c0, C);
+          flush_open_t<G, FULL>(ndst[j], ids.bot[j], tpend + 8u * G * (uint32_t)j + 4u * G, c.c0, C);
+        }
+        g_d += plane_stride;
+      }
+      __syncwarp();
+      if (d0 + 2 * ppf < p.D)
+        fill_run_samples_ho(s_tab[warp][buf], s_flg[warp][buf], p, c, d0 + 2 * ppf, ppf, lane, has_up, has_dn);
+      __syncwarp();
+    }
+    tmem_wait_st();
+    float* dst = p.g_feat + ref_off;
+    for (int i = 0; i < c.npix; ++i) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const P4 acc = tmem_ld4(tbase + 4u * (uint32_t)(i * G + g));
+        if (group_on<FULL>(c.c0, g, C)) red_add_p4(dst + i * C + 128 * g, acc);
+      }
+    }
+  }
+  tmem_free_cta<kCols>(&s_tmem, warp);
+}
+#endif  // MVSD_EXP_TMEM_PENDING
+
 // k in {1,2} only (k*kRun <= 32 samples per plane); other k use the pixel kernel.
 template <typename TIn, typename TG>
 static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
@@ -1716,6 +2066,21 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
     }                                                                                     \
     kern<<<grid, kRunThreads, dyn, st>>>(p);                                              \
   } while (0)
+#ifdef MVSD_EXP_TMEM_PENDING
+#define MVSD_RUNT(KM, GG, FU, NS)                                                           \
+  do {                                                                                    \
+    auto kern = sweep_bwd_runt_kernel<TIn, TG, KM, GG, FU, NS>;                            \
+    constexpr size_t dyn = runh_slot_bytes<KM, GG, NS, 2>();                              \
+    static bool attr_set = false;                                                         \
+    if (!attr_set) {                                                                      \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);  \
+      attr_set = true;                                                                    \
+    }                                                                                     \
+    kern<<<grid, kRunThreads, dyn, st>>>(p);                                              \
+  } while (0)
+#else
+#define MVSD_RUNT(KM, GG, FU, NS) MVSD_RUNS(KM, GG, FU, NS)      /* experiment not built: the default */
+#endif
 #define MVSD_RUNS(KM, GG, FU, NS)                                                           \
   do {                                                                                    \
     auto kern = sweep_bwd_runs_kernel<TIn, TG, KM, GG, FU, 3, NS>;                         \
@@ -1742,6 +2107,7 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   do {                                                                                    \
     if (tuning(5) == 8) MVSD_RUNH(KM, GG, FU, 2, 2);                                         \
     else if (tuning(5) == 11) MVSD_RUNF(KM, GG, FU, 2);                                      \
+    else if (tuning(5) == 17) MVSD_RUNT(KM, GG, FU, 2);                                      \
     else if (lean || tuning(5) == 16) MVSD_RUNS(KM, GG, FU, 2);                              \
     else if (tuning(5) == 14) sweep_bwd_runq2_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (tuning(5) == 7) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
@@ -1765,6 +2131,7 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
 #undef MVSD_RUNH
 #undef MVSD_RUNF
 #undef MVSD_RUNS
+#undef MVSD_RUNT
   count_launch();
   return check_launch("plane_sweep_bwd(run)");
 }
