@@ -157,8 +157,9 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // tuning key 5: 0/unset = slim row hand-off between the warps of a CTA with software-pipelined loads
-  // (sweep_bwd_runs, k <= 2: -25 % RED bytes), 14 = pipelined lean kernel without the hand-off
-  // (sweep_bwd_runq2), 7 = un-pipelined lean kernel (sweep_bwd_runq), 1 = pixel kernel, 2 = scalar
+  // (sweep_bwd_runs, k <= 2: -25 % RED bytes) for bf16 features, the un-pipelined lean kernel for fp32
+  // features (register budget, see launch_bwd_run_t); 16 = sweep_bwd_runs for every dtype, 14 = pipelined
+  // lean kernel without the hand-off (sweep_bwd_runq2), 7 = un-pipelined lean kernel (sweep_bwd_runq), 1 = pixel kernel, 2 = scalar
   // run-merging kernel, 3 = first packed run-merging kernel, 4 = block-merging kernel (TMEM + row cache),
   // 5 / 6 = two- / four-row blocks with two pending columns per source row (plane_sweep_bwd_rows.cu),
   // 8 / 11 = earlier hand-off kernels (8: decisions per pixel from the neighbouring rows' tables, CTA

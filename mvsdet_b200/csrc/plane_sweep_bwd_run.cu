@@ -2047,10 +2047,14 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
   const bool tm = tuning(4) == 0;          // tuning key 4: 0 = TMEM accumulators (default), 2 = shared memory
   const bool minb3 = tuning(4) != 1;       // tuning key 4: 1 = cap at 128 registers (4 CTAs/SM) instead of 168 (3)
   const bool packed = tuning(5) != 2;      // tuning key 5: 2 = scalar-math run kernel, 3 = packed
-  // default: slim row hand-off with software-pipelined loads (sweep_bwd_runs); 5=14: pipelined lean
-  // kernel without the hand-off (sweep_bwd_runq2); 5=7: un-pipelined lean kernel (sweep_bwd_runq);
-  // 5=3: first packed kernel (sweep_bwd_runp)
+  // default: slim row hand-off with software-pipelined loads (sweep_bwd_runs) for bf16 features; with
+  // fp32 features the raw loads of a pixel are 80 registers instead of 44 and the pipelined kernels
+  // spill (ptxas: 160 B of stack for sweep_bwd_runs<float>), so their default stays the un-pipelined
+  // lean kernel (sweep_bwd_runq, 168 registers, no spills).  5=16 forces sweep_bwd_runs, 5=14 the
+  // pipelined lean kernel without the hand-off (sweep_bwd_runq2), 5=7 sweep_bwd_runq, 5=3 the first
+  // packed kernel (sweep_bwd_runp).
   const bool lean = tuning(5) == 0 && tuning(4) == 0;
+  const bool slim_ok = sizeof(TIn) == 2;
 #ifdef MVSD_EXP_NORED
   { const int flag = tuning(6); cudaMemcpyToSymbolAsync(c_exp_nored, &flag, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
 #endif
@@ -2108,9 +2112,9 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
     if (tuning(5) == 8) MVSD_RUNH(KM, GG, FU, 2, 2);                                         \
     else if (tuning(5) == 11) MVSD_RUNF(KM, GG, FU, 2);                                      \
     else if (tuning(5) == 17) MVSD_RUNT(KM, GG, FU, 2);                                      \
-    else if (lean || tuning(5) == 16) MVSD_RUNS(KM, GG, FU, 2);                              \
+    else if ((lean && slim_ok) || tuning(5) == 16) MVSD_RUNS(KM, GG, FU, 2);                 \
     else if (tuning(5) == 14) sweep_bwd_runq2_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
-    else if (tuning(5) == 7) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
+    else if (lean || tuning(5) == 7) sweep_bwd_runq_kernel<TIn, TG, KM, GG, FU, MVSD_RUNQ_MINB><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && tm) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, true><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed && minb3) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 3, false><<<grid, kRunThreads, 0, st>>>(p); \
     else if (packed) sweep_bwd_runp_kernel<TIn, TG, KM, GG, FU, 4, false><<<grid, kRunThreads, 0, st>>>(p); \

@@ -240,7 +240,7 @@ def test_single_view_scene_variance_is_zero():
     assert float(var.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 11, 14])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 11, 14, 16])
 @pytest.mark.parametrize("case", ["scannet_tiny", "two_views", "wide_c"])
 def test_plane_sweep_bwd_variants(case, variant):
     """Every opt-in plane-sweep backward (mvsd_set_tuning key 5: 1 pixel kernel,
@@ -260,7 +260,7 @@ def test_plane_sweep_bwd_variants(case, variant):
 
 
 @pytest.mark.parametrize("hw", [(13, 21), (9, 7), (17, 40)])
-@pytest.mark.parametrize("variant", [0, 5, 7, 8, 11, 14])
+@pytest.mark.parametrize("variant", [0, 5, 7, 8, 11, 14, 16])
 def test_ragged_feature_map_sizes(hw, variant):
     """Feature maps whose height is not a multiple of the CTA's 4 rows and whose width is
     not a multiple of the 8-pixel run (partial runs, idle warps, hand-off with a missing
