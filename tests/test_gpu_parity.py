@@ -8,6 +8,8 @@ relative in fp32 (1e-2 with bf16 features).  Float comparisons use
 entries that cancel to ~0 (variance of three equal samples) are judged against
 the tensor's scale, as SURVEY.md "hard part 4" asks.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -18,6 +20,9 @@ from oracle import mvsdet_oracle as O
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4
+# experiment builds (e.g. -DMVSD_EXP_TMEM_PENDING, tuning 5=17): MVSD_TEST_EXTRA_VARIANTS=17 adds them to the
+# backward-variant parity tests; unset (the default) nothing changes
+EXTRA_VARIANTS = [int(x) for x in os.environ.get("MVSD_TEST_EXTRA_VARIANTS", "").split(",") if x.strip()]
 
 
 def _close(a, b, what, rtol=RTOL, atol_scale=1e-4, abs_floor=0.0):
@@ -240,7 +245,7 @@ def test_single_view_scene_variance_is_zero():
     assert float(var.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 11, 14, 16])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 11, 14, 16] + EXTRA_VARIANTS)
 @pytest.mark.parametrize("case", ["scannet_tiny", "two_views", "wide_c"])
 def test_plane_sweep_bwd_variants(case, variant):
     """Every opt-in plane-sweep backward (mvsd_set_tuning key 5: 1 pixel kernel,
@@ -260,7 +265,7 @@ def test_plane_sweep_bwd_variants(case, variant):
 
 
 @pytest.mark.parametrize("hw", [(13, 21), (9, 7), (17, 40)])
-@pytest.mark.parametrize("variant", [0, 5, 7, 8, 11, 14, 16])
+@pytest.mark.parametrize("variant", [0, 5, 7, 8, 11, 14, 16] + EXTRA_VARIANTS)
 def test_ragged_feature_map_sizes(hw, variant):
     """Feature maps whose height is not a multiple of the CTA's 4 rows and whose width is
     not a multiple of the 8-pixel run (partial runs, idle warps, hand-off with a missing
