@@ -58,9 +58,15 @@ const char* mvsd_build_info(void);          /* "sm_100a, nvcc 12.9, ..."     */
 const char* mvsd_status_string(int status);
 const char* mvsd_last_error(void);          /* thread-local, never NULL      */
 /* Tuning knobs for experiments (variant selection); returns previous value,
- * or -1 for an unknown key.  Keys: 0 = plane-sweep forward pixels per warp
- * (1,2,4), 1 = plane-sweep patch width in pixels, 2 = plane-sweep backward
- * pixels per warp (1,2).  0 = library default.                               */
+ * or -1 for an unknown key (keys 0..7).  Value 0 = library default for every
+ * key.  Keys: 3 = plane-sweep forward pixels per warp, 4 = plane-sweep backward
+ * accumulator placement / register cap of the first packed kernel, 5 =
+ * plane-sweep backward kernel (default: row hand-off with software-pipelined
+ * loads for bf16 features, lean run-merging kernel for fp32 features; the other
+ * values select the earlier kernels, listed in csrc/plane_sweep_bwd.cu and
+ * DESIGN.md section 5, all parity-tested), 6 = scalar-math forward /
+ * experiment switch, 7 = back-projection warps per CTA.  Not part of the
+ * drop-in contract: results are the same for every value.                    */
 int mvsd_set_tuning(int key, int value);
 /* Number of kernel launches issued through this library by the calling
  * process since load (bench.py's gpu_launches counter).                      */
