@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MVSD_ABI_VERSION 1
+#define MVSD_ABI_VERSION 2
 
 typedef enum {
   MVSD_OK = 0,
@@ -57,16 +57,14 @@ int mvsd_abi_version(void);
 const char* mvsd_build_info(void);          /* "sm_100a, nvcc 12.9, ..."     */
 const char* mvsd_status_string(int status);
 const char* mvsd_last_error(void);          /* thread-local, never NULL      */
-/* Tuning knobs for experiments (variant selection); returns previous value,
- * or -1 for an unknown key (keys 0..7).  Value 0 = library default for every
- * key.  Keys: 3 = plane-sweep forward pixels per warp, 4 = plane-sweep backward
- * accumulator placement / register cap of the first packed kernel, 5 =
- * plane-sweep backward kernel (default: row hand-off with software-pipelined
- * loads for bf16 features, lean run-merging kernel for fp32 features; the other
- * values select the earlier kernels, listed in csrc/plane_sweep_bwd.cu and
- * DESIGN.md section 5, all parity-tested), 6 = scalar-math forward /
- * experiment switch, 7 = back-projection warps per CTA.  Not part of the
- * drop-in contract: results are the same for every value.                    */
+/* TEST HOOK, not part of the drop-in contract and never called on the product
+ * path (the host layer, bench.py and smoke() do not use it): selects which of
+ * the built plane-sweep backward kernels serves k in {1,2} so the parity tests
+ * can exercise both.  key 5: 0 = default (run-merging kernels: row hand-off
+ * for bf16 features, lean kernel for fp32 features), 1 = the generic
+ * pixel-per-warp kernel that otherwise serves k = 3, 4.  Results agree to fp32
+ * summation order.  Process-wide atomic; returns the previous value, or -1 for
+ * an unknown key (keys 0..7; only 5 is read).                                */
 int mvsd_set_tuning(int key, int value);
 /* Number of kernel launches issued through this library by the calling
  * process since load (bench.py's gpu_launches counter).                      */
@@ -81,6 +79,28 @@ int mvsd_pack_nchw_to_nhwc(const float* src, void* dst, int dst_dtype,
 int mvsd_unpack_nhwc_to_nchw(const float* src, float* dst, int accumulate,
                              int V, int C, int H, int W, void* stream);
 
+/* ---- a1, a2, a8: per-scene camera geometry in one launch ----------------- *
+ * Replaces, per scene, mvsdet.py:43-104 + :432-434 (nearest-pose ids),
+ * :249-264 (collect_proj), mvs_models/module.py:116-118 (src_proj @
+ * inverse(ref_proj)) and :1124-1156 (_compute_projection).  The HOST keeps two
+ * ATen calls whose bits the variance volume depends on:
+ * ref_proj = K_feat @ w2c and inverse(ref_proj); everything else is here.
+ *   w2c       [V,4,4] fp32 world-to-camera extrinsics (img_meta lidar2img)
+ *   k_feat    [4,4] (per_view_k = 0) or [V,4,4] (per_view_k = 1) fp32
+ *             feature-level intrinsics: rows 0-1 already divided by
+ *             ratio = ori_h / (img_h / stride) (mvsdet.py:422-428)
+ *   ref_proj  [V,4,4] fp32, inv_ref [V,4,4] fp32 = inverse(ref_proj)
+ *   k         neighbours per view, <= min(4, V-1) (reference: min(2, V-1))
+ *   ref_begin, n_ref   reference views [ref_begin, ref_begin+n_ref) whose rows
+ *             are produced (view sharding; 0, V for a whole scene)
+ * Outputs (device): nbr_ids [n_ref,k] int32 (nearest first, self excluded,
+ * indices into the V views), hom [n_ref,k,12] fp32, projection [n_ref,3,4].
+ * V <= 1024.  Rounding reproduces ATen's CPU matmul kernels (csrc/scene_setup.cu). */
+int mvsd_scene_setup(const float* w2c, const float* k_feat, int per_view_k,
+                     const float* ref_proj, const float* inv_ref,
+                     int32_t* nbr_ids, float* hom, float* projection,
+                     int V, int k, int ref_begin, int n_ref, void* stream);
+
 /* ---- a3+a4: fused plane-sweep variance ---------------------------------- *
  * Replaces mvsdet.py:439-467 (ref_volume repeat, k x homo_warping
  * [mvs_models/module.py:105-146], sum / square-sum, variance).
@@ -94,13 +114,17 @@ int mvsd_unpack_nhwc_to_nchw(const float* src, float* dst, int accumulate,
  * View sharding: V counts the REFERENCE views of this call; reference view v
  * reads feat[ref_begin + v] while nbr_ids index feat directly, so a rank can
  * sweep a slice [ref_begin, ref_begin+V) of a scene whose feature maps are all
- * resident (ref_begin = 0 for a whole scene).                                */
+ * resident (ref_begin = 0 for a whole scene).
+ * n_feat_views = number of views feat holds: ref_begin + V must not exceed it
+ * (MVSD_ERR_INVALID_ARG), and a neighbour id outside [0, n_feat_views) is never
+ * dereferenced -- that neighbour contributes no sample (forward) and receives
+ * no gradient (backward), like a warp that falls outside the map.            */
 int mvsd_plane_sweep_fwd(const void* feat, int feat_dtype,
                          const int32_t* nbr_ids, const float* hom,
                          const float* depth_values,
                          void* out, int out_dtype, int out_layout,
                          int V, int C, int D, int H, int W, int k, int ref_begin,
-                         void* stream);
+                         int n_feat_views, void* stream);
 /* Backward of the above (what autograd computes through mvsdet.py:439-467):
  *   g_out   dL/dvariance, same layout as `out`, of g_dtype
  *   g_feat  nhwc fp32, same extent as feat; contributions are ADDED (caller
@@ -110,18 +134,20 @@ int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout,
                          const int32_t* nbr_ids, const float* hom,
                          const float* depth_values, float* g_feat,
                          int V, int C, int D, int H, int W, int k, int ref_begin,
-                         void* stream);
+                         int n_feat_views, void* stream);
 
 /* ---- a3 alone: homo_warping (mvs_models/module.py:105-146) --------------- *
- *   src  nhwc [B,H,W,C]; hom [B,12]; depth_values [B,D]; out [B,D,H,W,C].   */
+ *   src  nhwc [B,H,W,C]; hom [B,12]; out [B,D,H,W,C];
+ *   depth_values [B,D], or per-pixel [B,D,H,W] when depth_per_pixel != 0
+ *   (module.py:130-133; MVSDet itself only uses the [B,D] form).             */
 int mvsd_homo_warp_fwd(const void* src, int src_dtype, const float* hom,
                        const float* depth_values, void* out, int out_dtype,
                        int out_layout, int B, int C, int D, int H, int W,
-                       void* stream);
+                       int depth_per_pixel, void* stream);
 int mvsd_homo_warp_bwd(const void* g_out, int g_dtype, int g_layout,
                        const float* hom, const float* depth_values,
                        float* g_src, int B, int C, int D, int H, int W,
-                       void* stream);
+                       int depth_per_pixel, void* stream);
 
 /* ---- a5-a7: softmax / sigmoid / top-k / depth expectation ---------------- *
  * Replaces mvsdet.py:470-482, sample_depth_prob (:266-283) and
@@ -134,24 +160,50 @@ int mvsd_homo_warp_bwd(const void* g_out, int g_dtype, int g_layout,
  *   est_depth, est_dens    [V,T,H,W] fp32;  est_idx [V,T,H,W] int64
  *   depth_coding           [V,H,W] fp32 (may be NULL)
  * Top-k order: descending probability, ties -> lowest plane index first.
+ * A pixel with NaN probabilities gets the lowest planes not yet taken (indices
+ * stay distinct).  depth_coding is summed in plane order (the reference sums
+ * in probability-sorted order): equal to fp32 summation rounding, ~1e-6.
  * raw != 0: channel 0 of cost_out already holds probabilities and channel 1
  * offsets in [0,1] (the stand-alone sample_depth_prob / compute_avg_depth API);
- * softmax / sigmoid are skipped, forward and backward.                        */
+ * softmax / sigmoid are skipped, forward and backward.
+ * NVS-branch epilogue (all optional, NULL = skip):
+ *   ray_intrinsics  [4,4] or (ray_per_view) [V,4,4] feature-level intrinsics
+ *   opacity         [V,H,W] = max_d prob_volume            (mvsdet.py:579)
+ *   depth_scale     [V,H,W] z of the unit ray through each pixel
+ *                   (compute_depth_scale[_MultiIntrin], mvsdet.py:1158-1218)
+ *   est_ray_depth   [V,T,H,W] = est_depth / (depth_scale + 1e-8)     (:494)
+ *   ray_depth_coding [V,H,W]  = depth_coding / (depth_scale + 1e-8)  (:583)   */
 int mvsd_depth_topk_fwd(const float* cost_out, int64_t s_v, int64_t s_c,
                         int64_t s_d, int64_t s_p,
                         float* prob_volume, float* off_pred, float* est_depth,
                         float* est_dens, int64_t* est_idx, float* depth_coding,
+                        const float* ray_intrinsics, int ray_per_view,
+                        float* opacity, float* depth_scale, float* est_ray_depth,
+                        float* ray_depth_coding,
                         float near, float interval, int raw,
                         int V, int D, int H, int W, int T, void* stream);
-/* Backward: any of the four upstream gradients may be NULL (treated as 0).
+/* Backward: any of the upstream gradients may be NULL (treated as 0).
  *   g_cost_out  [V,2,D,H,W] fp32 contiguous, fully overwritten.              */
 int mvsd_depth_topk_bwd(const float* cost_out, int64_t s_v, int64_t s_c,
                         int64_t s_d, int64_t s_p, const int64_t* est_idx,
                         const float* g_prob_volume, const float* g_off_pred,
                         const float* g_est_depth, const float* g_est_dens,
-                        const float* g_depth_coding, float* g_cost_out,
+                        const float* g_depth_coding,
+                        const float* ray_intrinsics, int ray_per_view,
+                        const float* g_est_ray_depth, const float* g_ray_depth_coding,
+                        float* g_cost_out,
                         float near, float interval, int raw,
                         int V, int D, int H, int W, int T, void* stream);
+
+/* compute_depth_scale / compute_depth_scale_MultiIntrin alone (mvsdet.py:1158-1218):
+ * depth_scale [V,H,W] from [4,4] or (per_view) [V,4,4] feature-level intrinsics. */
+int mvsd_ray_depth_scale(const float* intrinsics, int per_view, float* depth_scale,
+                         int V, int H, int W, void* stream);
+/* process_rgb_raw (mvsdet.py:319-333): bilinear 1/4 down-sampling
+ * (align_corners=False) of rgb [V,3,H,W] fp32 for the views src_ids [n_ids]
+ * int64 (NULL = views 0..n_ids-1), cropped to [h,w], written as [n_ids,h*w,3]. */
+int mvsd_rgb_downsample4(const float* rgb, const int64_t* src_ids, int n_ids, float* out,
+                         int V, int H, int W, int h, int w, void* stream);
 
 /* ---- a10+a11: probabilistic voxel back-projection ------------------------ *
  * Replaces backproject_Weigh (mvsdet.py:1372-1492) and the view aggregation

@@ -10,6 +10,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MVSDET_B200_LIB") or os.path.join(HERE, "lib", "libmvsdet_b200.so")
 
+ABI_VERSION = 2
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 F32, BF16 = 0, 1
 CHANNELS_LAST, CHANNELS_FIRST = 0, 1
@@ -27,14 +28,17 @@ SIGNATURES = {
     "mvsd_launch_count": ([], _l),
     "mvsd_pack_nchw_to_nhwc": ([_p, _p, _i, _i, _i, _i, _i, _p], _i),
     "mvsd_unpack_nhwc_to_nchw": ([_p, _p, _i, _i, _i, _i, _i, _p], _i),
-    "mvsd_plane_sweep_fwd": ([_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
-    "mvsd_plane_sweep_bwd": ([_p, _i, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p], _i),
-    "mvsd_homo_warp_fwd": ([_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p], _i),
-    "mvsd_homo_warp_bwd": ([_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p], _i),
-    "mvsd_depth_topk_fwd": ([_p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _f, _f, _i,
-                             _i, _i, _i, _i, _i, _p], _i),
-    "mvsd_depth_topk_bwd": ([_p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _f, _f, _i,
-                             _i, _i, _i, _i, _i, _p], _i),
+    "mvsd_scene_setup": ([_p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
+    "mvsd_plane_sweep_fwd": ([_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "mvsd_plane_sweep_bwd": ([_p, _i, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "mvsd_homo_warp_fwd": ([_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "mvsd_homo_warp_bwd": ([_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p], _i),
+    "mvsd_depth_topk_fwd": ([_p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p,
+                             _f, _f, _i, _i, _i, _i, _i, _i, _p], _i),
+    "mvsd_depth_topk_bwd": ([_p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p,
+                             _f, _f, _i, _i, _i, _i, _i, _i, _p], _i),
+    "mvsd_ray_depth_scale": ([_p, _i, _p, _i, _i, _i, _p], _i),
+    "mvsd_rgb_downsample4": ([_p, _p, _i, _p, _i, _i, _i, _i, _i, _p], _i),
     "mvsd_backproject_fwd": ([_p, _i, _i, _i, _p, _p, _p, _p, _l, _l, _l, _l, _f, _i, _p, _i,
                               _p, _p, _p, _i, _i, _i, _i, _i, _i, _p], _i),
     "mvsd_backproject_bwd": ([_p, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _l, _l, _l, _l,
@@ -66,7 +70,7 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)          # AttributeError if a symbol is missing
                 fn.argtypes = argtypes
                 fn.restype = restype
-            if lib.mvsd_abi_version() != 1:
+            if lib.mvsd_abi_version() != ABI_VERSION:
                 raise MvsdError("libmvsdet_b200.so ABI version mismatch; rebuild")
             _lib = lib
     return _lib

@@ -22,13 +22,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvsdet_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
-SOURCES = ("capi.cu", "pack.cu", "plane_sweep_fwd.cu", "plane_sweep_bwd.cu", "plane_sweep_bwd_run.cu", "plane_sweep_bwd_blk.cu", "plane_sweep_bwd_rows.cu",
-           "depth_topk.cu",
-           "backproject.cu", "voxel_p2p.cu")
+SOURCES = ("capi.cu", "pack.cu", "scene_setup.cu", "plane_sweep_fwd.cu", "plane_sweep_bwd.cu",
+           "plane_sweep_bwd_run.cu", "depth_topk.cu", "backproject.cu", "voxel_p2p.cu")
 HEADERS = (os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "plane_sweep.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "mvsdet_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-Xfatbin", "-compress-all"]
 # experiment builds only (e.g. MVSD_EXTRA_NVCC_FLAGS="-DMVSD_KRUN=16"); part of the object digest
 NVCC_FLAGS += os.environ.get("MVSD_EXTRA_NVCC_FLAGS", "").split()
 
@@ -50,7 +49,11 @@ def _digest(paths) -> str:
 
 
 def _sources():
-    return [os.path.join(CSRC, s) for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
+    paths = [os.path.join(CSRC, s) for s in SOURCES]
+    missing = [p for p in paths if not os.path.isfile(p)]
+    if missing:
+        raise RuntimeError(f"mvsdet_b200 build: listed sources are missing: {missing}")
+    return paths
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

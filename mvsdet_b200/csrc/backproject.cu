@@ -302,10 +302,8 @@ static int launch_bp_warps(const BpParams& p, int mode, bool cfirst, cudaStream_
 
 template <typename TIn, int G, bool BWD>
 static int launch_bp_mode(const BpParams& p, int mode, bool cfirst, cudaStream_t st) {
-  const int t = tuning(7);               // tuning key 7: warps per CTA (8, 16, 32); 0 = default
-  if (t == 8) return launch_bp_warps<TIn, G, BWD, 8>(p, mode, cfirst, st);
-  if (t == 32) return launch_bp_warps<TIn, G, BWD, 32>(p, mode, cfirst, st);
-  return launch_bp_warps<TIn, G, BWD, 16>(p, mode, cfirst, st);   // measured best on B200 (fwd 37 us, bwd 46 us)
+  // 16 warps per CTA: measured best on B200 (fwd 37 us, bwd 46 us; 8 and 32 warps were slower)
+  return launch_bp_warps<TIn, G, BWD, 16>(p, mode, cfirst, st);
 }
 
 template <bool BWD>

@@ -22,11 +22,18 @@ int fail(int status, const char* fmt, ...) {
   return status;
 }
 
+// Launch-configuration errors of OUR launch are non-sticky: they are reported through the status
+// and cleared, so they do not resurface in the caller's next CUDA call.  A sticky error (an
+// asynchronous fault of an earlier kernel, possibly the caller's own) cannot be cleared by
+// cudaGetLastError and stays visible to the caller; the message says which case it is.
 int check_launch(const char* what) {
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess)
-    return fail(MVSD_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
-  return MVSD_OK;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e == cudaSuccess) return MVSD_OK;
+  cudaGetLastError();
+  const bool sticky = cudaPeekAtLastError() != cudaSuccess;
+  return fail(MVSD_ERR_CUDA, "%s: %s (%s)%s", what, cudaGetErrorName(e), cudaGetErrorString(e),
+              sticky ? " -- sticky context error, raised by an earlier kernel (not necessarily one of "
+                       "this library's)" : "");
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

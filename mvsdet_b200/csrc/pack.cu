@@ -88,6 +88,32 @@ __global__ void __launch_bounds__(256) unpack_kernel(const float* __restrict__ s
   }
 }
 
+// process_rgb_raw (mvsdet.py:319-333): F.interpolate(rgb[src_id], scale_factor=1/4, 'bilinear'),
+// crop to [h,w], laid out as [n, h*w, 3].  With scale 1/4 and align_corners=False the source
+// coordinate of output pixel x is 4x + 1.5: the sample is the mean of the 2x2 block at (4x+1, 4y+1),
+// evaluated in ATen's order  hl0*(wl0*a + wl1*b) + hl1*(wl0*c + wl1*d)  with all four lambdas 0.5.
+__global__ void __launch_bounds__(128) rgb_downsample4_kernel(const float* __restrict__ src,
+                                                              const int64_t* __restrict__ ids,
+                                                              float* __restrict__ dst, int H, int W,
+                                                              int h, int w) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (pix >= h * w) return;
+  const int y = pix / w, x = pix - y * w;
+  const int64_t v = ids ? ids[n] : n;
+  const int y0 = 4 * y + 1, x0 = 4 * x + 1;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* s = src + ((size_t)v * 3 + c) * H * W;
+    const float a = __ldg(s + (size_t)y0 * W + x0), b = __ldg(s + (size_t)y0 * W + x1);
+    const float cc = __ldg(s + (size_t)y1 * W + x0), d = __ldg(s + (size_t)y1 * W + x1);
+    const float top = __fadd_rn(__fmul_rn(0.5f, a), __fmul_rn(0.5f, b));
+    const float bot = __fadd_rn(__fmul_rn(0.5f, cc), __fmul_rn(0.5f, d));
+    dst[((size_t)n * h * w + pix) * 3 + c] = __fadd_rn(__fmul_rn(0.5f, top), __fmul_rn(0.5f, bot));
+  }
+}
+
 }  // namespace mvsd
 
 using namespace mvsd;
@@ -120,4 +146,18 @@ extern "C" int mvsd_unpack_nhwc_to_nchw(const float* src, float* dst, int accumu
   unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, accumulate, C, HW);
   count_launch();
   return check_launch("unpack_nhwc_to_nchw");
+}
+
+extern "C" int mvsd_rgb_downsample4(const float* rgb, const int64_t* src_ids, int n_ids, float* out,
+                                    int V, int H, int W, int h, int w, void* stream) {
+  if (V <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0 || n_ids <= 0)
+    return fail(MVSD_ERR_INVALID_ARG, "rgb_downsample4: non-positive dimension");
+  if (!rgb || !out) return fail(MVSD_ERR_INVALID_ARG, "rgb_downsample4: null pointer");
+  if (h > H / 4 || w > W / 4)
+    return fail(MVSD_ERR_INVALID_ARG, "rgb_downsample4: crop [%d,%d] exceeds the quarter-size map of [%d,%d]", h, w, H, W);
+  if (n_ids > 65535) return fail(MVSD_ERR_UNSUPPORTED, "rgb_downsample4: %d views > 65535", n_ids);
+  dim3 grid((h * w + 127) / 128, n_ids);
+  rgb_downsample4_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(rgb, src_ids, out, H, W, h, w);
+  count_launch();
+  return check_launch("rgb_downsample4");
 }

@@ -41,12 +41,14 @@ struct SweepParams {
   const void* feat;        // nhwc features
   const int32_t* nbr;      // [V,k] or nullptr (warp-only: source = same index)
   const float* hom;        // [V,k,12]
-  const float* depth;      // [V,D]
+  const float* depth;      // [V,D], or [V,D,H,W] when depth_per_pixel (stand-alone warp only)
   void* out;               // fwd output [V,D,H,W,C]
   const void* g_out;       // bwd upstream gradient, same layout
   float* g_feat;           // bwd: nhwc fp32, accumulated with RED
   int V, C, D, H, W, k;
   int ref_begin;           // feat index of reference view 0 (view sharding)
+  int n_feat;              // views held by feat: neighbour ids outside [0, n_feat) give no sample
+  int depth_per_pixel;     // homo_warping's [B,D,H,W] depth_values branch (module.py:130-133)
   int tiles_x, tiles_y, slices;
 };
 
@@ -70,6 +72,14 @@ __device__ __forceinline__ SweepCoord sweep_coord(const SweepParams& p, int warp
   return c;
 }
 
+// A neighbour id outside the feature tensor (stale or un-rebased ids against a compact / sliced
+// buffer) must neither be read nor -- in the backward -- be the target of a RED: such a
+// neighbour simply contributes no sample, like a warp that lands outside the map.
+__device__ __forceinline__ bool nbr_in_range(const SweepParams& p, int v, int j) {
+  if (p.nbr == nullptr) return true;              // stand-alone warp: source = same index
+  return (unsigned)__ldg(p.nbr + (size_t)v * p.k + j) < (unsigned)p.n_feat;
+}
+
 // One pass of sample geometry for this warp's pixel: lane s computes the sample
 // of (plane d0 + s / k, neighbour s % k).
 __device__ __forceinline__ void fill_samples(WarpSample* tab, const SweepParams& p,
@@ -81,13 +91,14 @@ __device__ __forceinline__ void fill_samples(WarpSample* tab, const SweepParams&
     WarpSample s;
     s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
     s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
-    if (d < p.D) {
+    if (d < p.D && nbr_in_range(p, c.v, j)) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
       float mm[12];
 #pragma unroll
       for (int t = 0; t < 12; ++t) mm[t] = __ldg(m + t);
-      s = make_warp_sample(mm, (float)c.x, (float)c.y, __ldg(p.depth + (size_t)c.v * p.D + d),
-                           p.H, p.W, p.C);
+      const size_t di = (size_t)c.v * p.D + d;
+      const float depth = p.depth_per_pixel ? __ldg(p.depth + (di * p.H + c.y) * p.W + c.x) : __ldg(p.depth + di);
+      s = make_warp_sample(mm, (float)c.x, (float)c.y, depth, p.H, p.W, p.C);
     }
     tab[lane] = s;
   }

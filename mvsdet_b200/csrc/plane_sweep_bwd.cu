@@ -117,27 +117,20 @@ static int launch_bwd_k(SweepParams& p, cudaStream_t st) {
   dim3 grid;
   const int G = sweep_groups(p.C);
   if (!sweep_grid(p, G, grid)) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_bwd: grid too large");
-  const bool full = p.C % (128 * G) == 0;
-  const int kmax = WARP_ONLY ? 1 : (p.k <= 1 ? 1 : (p.k == 2 ? 2 : 4));
-#define MVSD_BWD(KM, GG, FU) \
-  sweep_bwd_kernel<TIn, TG, KM, GG, FU, WARP_ONLY><<<grid, kSweepThreads, 0, st>>>(p)
-#define MVSD_BWD_G(KM)                                                            \
-  do {                                                                            \
-    if (G == 2) { if (full) MVSD_BWD(KM, 2, true); else MVSD_BWD(KM, 2, false); } \
-    else { if (full) MVSD_BWD(KM, 1, true); else MVSD_BWD(KM, 1, false); }        \
-  } while (0)
-  if (kmax == 1) MVSD_BWD_G(1);
-  else if (kmax == 2) MVSD_BWD_G(2);
-  else MVSD_BWD_G(4);
-#undef MVSD_BWD_G
+  // generic fallback (k = 3, 4, the stand-alone warp, and the test hook): one instantiation per
+  // dtype and channel-group count, every k <= 4 and ragged C handled by predication
+#define MVSD_BWD(KM, GG) sweep_bwd_kernel<TIn, TG, KM, GG, false, WARP_ONLY><<<grid, kSweepThreads, 0, st>>>(p)
+  if constexpr (WARP_ONLY) {
+    if (G == 2) MVSD_BWD(1, 2); else MVSD_BWD(1, 1);
+  } else {
+    if (G == 2) MVSD_BWD(4, 2); else MVSD_BWD(4, 1);
+  }
 #undef MVSD_BWD
   count_launch();
   return check_launch("plane_sweep_bwd");
 }
 
 int launch_bwd_run(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st);
-int launch_bwd_blk(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st);
-int launch_bwd_rows(SweepParams& p, int rows, int feat_dtype, int g_dtype, cudaStream_t st);
 
 }  // namespace mvsd
 
@@ -146,31 +139,25 @@ using namespace mvsd;
 extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout, const void* feat,
                                     int feat_dtype, const int32_t* nbr_ids, const float* hom,
                                     const float* depth_values, float* g_feat, int V, int C, int D,
-                                    int H, int W, int k, int ref_begin, void* stream) {
+                                    int H, int W, int k, int ref_begin, int n_feat_views,
+                                    void* stream) {
   if (int e = sweep_check("plane_sweep_bwd", V, C, D, H, W, k, g_layout)) return e;
   if (!g_out || !feat || !g_feat || !depth_values || (k > 0 && (!nbr_ids || !hom)))
     return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_bwd: null pointer");
-  if (ref_begin < 0) return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_bwd: negative ref_begin");
+  if (ref_begin < 0 || (long long)ref_begin + V > n_feat_views)
+    return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_bwd: reference views [%d, %d) exceed the %d feature views",
+                ref_begin, ref_begin + V, n_feat_views);
   SweepParams p{};
   p.feat = feat; p.nbr = nbr_ids; p.hom = hom; p.depth = depth_values; p.g_out = g_out;
   p.g_feat = g_feat;
-  p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin;
+  p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin; p.n_feat = n_feat_views;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // tuning key 5: 0/unset = slim row hand-off between the warps of a CTA with software-pipelined loads
-  // (sweep_bwd_runs, k <= 2: -25 % RED bytes) for bf16 features, the un-pipelined lean kernel for fp32
-  // features (register budget, see launch_bwd_run_t); 16 = sweep_bwd_runs for every dtype, 14 = pipelined
-  // lean kernel without the hand-off (sweep_bwd_runq2), 7 = un-pipelined lean kernel (sweep_bwd_runq), 1 = pixel kernel, 2 = scalar
-  // run-merging kernel, 3 = first packed run-merging kernel, 4 = block-merging kernel (TMEM + row cache),
-  // 5 / 6 = two- / four-row blocks with two pending columns per source row (plane_sweep_bwd_rows.cu),
-  // 8 / 11 = earlier hand-off kernels (8: decisions per pixel from the neighbouring rows' tables, CTA
-  // barrier per refill; 11: decisions at table-fill time, un-pipelined).  Every variant is parity-tested
-  // (tests/test_gpu_parity.py); measured times, and the variants that were measured and removed
-  // (deeper queues, L1 prefetch of the next pixel), in DESIGN.md section 5.
-  const int variant = tuning(5);
-  if ((k == 1 || k == 2) && variant == 4) return launch_bwd_blk(p, feat_dtype, g_dtype, st);
-  if ((k == 1 || k == 2) && (variant == 5 || variant == 6))
-    return launch_bwd_rows(p, variant == 5 ? 2 : 4, feat_dtype, g_dtype, st);
-  if ((k == 1 || k == 2) && variant != 1) return launch_bwd_run(p, feat_dtype, g_dtype, st);
+  // Kernel selection.  k in {1, 2} (the reference uses k = min(2, V-1), mvsdet.py:432): the
+  // run-merging kernels of plane_sweep_bwd_run.cu -- row hand-off + pipelined loads for bf16
+  // features, the lean kernel for fp32 features.  Any other k (and the stand-alone warp): the
+  // pixel-per-warp kernel above.  mvsd_set_tuning(5, 1) is a TEST hook, never used on the product
+  // path: it sends k in {1, 2} to the pixel kernel too.
+  if ((k == 1 || k == 2) && tuning(5) != 1) return launch_bwd_run(p, feat_dtype, g_dtype, st);
   if (feat_dtype == MVSD_F32 && g_dtype == MVSD_F32) return launch_bwd_k<float, float, false>(p, st);
   if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_F32)
     return launch_bwd_k<__nv_bfloat16, float, false>(p, st);
@@ -181,14 +168,15 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
 
 extern "C" int mvsd_homo_warp_bwd(const void* g_out, int g_dtype, int g_layout, const float* hom,
                                   const float* depth_values, float* g_src, int B, int C, int D,
-                                  int H, int W, void* stream) {
+                                  int H, int W, int depth_per_pixel, void* stream) {
   if (int e = sweep_check("homo_warp_bwd", B, C, D, H, W, 1, g_layout)) return e;
   if (!g_out || !hom || !depth_values || !g_src)
     return fail(MVSD_ERR_INVALID_ARG, "homo_warp_bwd: null pointer");
   SweepParams p{};
   p.feat = nullptr; p.nbr = nullptr; p.hom = hom; p.depth = depth_values; p.g_out = g_out;
   p.g_feat = g_src;
-  p.V = B; p.C = C; p.D = D; p.H = H; p.W = W; p.k = 1; p.ref_begin = 0;
+  p.V = B; p.C = C; p.D = D; p.H = H; p.W = W; p.k = 1; p.ref_begin = 0; p.n_feat = B;
+  p.depth_per_pixel = depth_per_pixel ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (g_dtype == MVSD_F32) return launch_bwd_k<float, float, true>(p, st);
   if (g_dtype == MVSD_BF16) return launch_bwd_k<float, __nv_bfloat16, true>(p, st);

@@ -233,12 +233,8 @@ int sweep_check(const char* who, int V, int C, int D, int H, int W, int k, int l
 }
 
 // Channel groups (of 128) per warp: 2 keeps all 256 FPN channels of a tap in one
-// warp (fewest instructions per byte); tuning key 3 overrides (1, 2).
-int sweep_groups(int C) {
-  const int t = tuning(3);
-  if (t == 1 || t == 2) return t;
-  return C > 128 ? 2 : 1;
-}
+// warp (fewest instructions per byte).
+int sweep_groups(int C) { return C > 128 ? 2 : 1; }
 
 bool sweep_grid(SweepParams& p, int G, dim3& grid) {
   p.tiles_x = (p.W + kPatchW - 1) / kPatchW;
@@ -257,20 +253,27 @@ static int launch_fwd_k(SweepParams& p, cudaStream_t st) {
   if (!sweep_grid(p, G, grid)) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_fwd: grid too large");
   const bool full = p.C % (128 * G) == 0;
   const int kmax = WARP_ONLY ? 1 : (p.k <= 1 ? 1 : (p.k == 2 ? 2 : 4));
-  const bool packed = !WARP_ONLY && tuning(6) != 1;   // tuning key 6: 1 = scalar-math kernel
 #define MVSD_FWD(KM, GG, FU)                                                           \
   do {                                                                                 \
-    if (packed) sweep_fwd_p_kernel<TIn, TOut, KM, GG, FU><<<grid, kSweepThreads, 0, st>>>(p); \
-    else sweep_fwd_kernel<TIn, TOut, KM, GG, FU, WARP_ONLY><<<grid, kSweepThreads, 0, st>>>(p); \
+    if constexpr (WARP_ONLY)                                                           \
+      sweep_fwd_kernel<TIn, TOut, KM, GG, FU, true><<<grid, kSweepThreads, 0, st>>>(p); \
+    else                                                                               \
+      sweep_fwd_p_kernel<TIn, TOut, KM, GG, FU><<<grid, kSweepThreads, 0, st>>>(p);    \
   } while (0)
 #define MVSD_FWD_G(KM)                                                            \
   do {                                                                            \
     if (G == 2) { if (full) MVSD_FWD(KM, 2, true); else MVSD_FWD(KM, 2, false); } \
     else { if (full) MVSD_FWD(KM, 1, true); else MVSD_FWD(KM, 1, false); }        \
   } while (0)
-  if (kmax == 1) MVSD_FWD_G(1);
-  else if (kmax == 2) MVSD_FWD_G(2);
-  else MVSD_FWD_G(4);
+  if constexpr (WARP_ONLY) {
+    MVSD_FWD_G(1);                        // stand-alone warp: the scalar kernel, one source
+  } else {
+    // k = 2 is the reference's configuration (mvsdet.py:432) and gets the un-predicated
+    // instantiation; k = 0, 1 (one- and two-view scenes) and k = 3, 4 share the predicated ones
+    if (kmax == 2) MVSD_FWD_G(2);
+    else if (kmax == 1) { if (G == 2) MVSD_FWD(1, 2, false); else MVSD_FWD(1, 1, false); }
+    else { if (G == 2) MVSD_FWD(4, 2, false); else MVSD_FWD(4, 1, false); }
+  }
 #undef MVSD_FWD_G
 #undef MVSD_FWD
   count_launch();
@@ -296,26 +299,29 @@ using namespace mvsd;
 extern "C" int mvsd_plane_sweep_fwd(const void* feat, int feat_dtype, const int32_t* nbr_ids,
                                     const float* hom, const float* depth_values, void* out,
                                     int out_dtype, int out_layout, int V, int C, int D, int H,
-                                    int W, int k, int ref_begin, void* stream) {
+                                    int W, int k, int ref_begin, int n_feat_views, void* stream) {
   if (int e = sweep_check("plane_sweep_fwd", V, C, D, H, W, k, out_layout)) return e;
   if (!feat || !out || !depth_values || (k > 0 && (!nbr_ids || !hom)))
     return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_fwd: null pointer");
-  if (ref_begin < 0) return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_fwd: negative ref_begin");
+  if (ref_begin < 0 || (long long)ref_begin + V > n_feat_views)
+    return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_fwd: reference views [%d, %d) exceed the %d feature views",
+                ref_begin, ref_begin + V, n_feat_views);
   SweepParams p{};
   p.feat = feat; p.nbr = nbr_ids; p.hom = hom; p.depth = depth_values; p.out = out;
-  p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin;
+  p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin; p.n_feat = n_feat_views;
   return launch_fwd<false>(p, feat_dtype, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mvsd_homo_warp_fwd(const void* src, int src_dtype, const float* hom,
                                   const float* depth_values, void* out, int out_dtype,
                                   int out_layout, int B, int C, int D, int H, int W,
-                                  void* stream) {
+                                  int depth_per_pixel, void* stream) {
   if (int e = sweep_check("homo_warp_fwd", B, C, D, H, W, 1, out_layout)) return e;
   if (!src || !hom || !depth_values || !out)
     return fail(MVSD_ERR_INVALID_ARG, "homo_warp_fwd: null pointer");
   SweepParams p{};
   p.feat = src; p.nbr = nullptr; p.hom = hom; p.depth = depth_values; p.out = out;
-  p.V = B; p.C = C; p.D = D; p.H = H; p.W = W; p.k = 1; p.ref_begin = 0;
+  p.V = B; p.C = C; p.D = D; p.H = H; p.W = W; p.k = 1; p.ref_begin = 0; p.n_feat = B;
+  p.depth_per_pixel = depth_per_pixel ? 1 : 0;
   return launch_fwd<true>(p, src_dtype, out_dtype, static_cast<cudaStream_t>(stream));
 }

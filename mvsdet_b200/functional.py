@@ -5,6 +5,8 @@ Same names, argument meaning, return shapes and error behaviour as
   sample_depth_prob       MVSDet.sample_depth_prob, mvsdet.py:266-283
   compute_avg_depth       MVSDet.compute_avg_depth, mvsdet.py:298-317
   backproject_Weigh       mvsdet.py:1372-1492
+  compute_depth_scale[_MultiIntrin]   MVSDet.compute_depth_scale*, mvsdet.py:1158-1218
+  process_rgb_raw         MVSDet.process_rgb_raw, mvsdet.py:319-333
   get_points, knn, get_nearest_pose_ids, collect_proj, _compute_projection
 but every tensor op runs in the sm_100a kernels of this package (ops.py).  The
 methods of the reference that read ``self`` take the same values as keyword
@@ -28,7 +30,8 @@ _compute_projection = G.compute_projection
 
 __all__ = ["homo_warping", "sample_depth_prob", "compute_avg_depth", "backproject_Weigh",
            "knn", "get_nearest_pose_ids", "collect_proj", "get_points",
-           "_compute_projection"]
+           "_compute_projection", "compute_depth_scale", "compute_depth_scale_MultiIntrin",
+           "process_rgb_raw"]
 
 
 def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.Tensor,
@@ -37,9 +40,8 @@ def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.
     -> warped [B,C,D,H,W] (channels_last_3d memory).  No gradient reaches the
     projection matrices or the depths (the reference builds the grid under
     no_grad, module.py:115)."""
-    if depth_values.dim() != 2:
-        raise ValueError("per-pixel depth_values [B,D,H,W] (module.py:130-133) is not used by "
-                         "MVSDet and not implemented")
+    if depth_values.dim() not in (2, 4):
+        raise ValueError("depth_values must be [B,D] or per-pixel [B,D,H,W] (module.py:126-133)")
     with torch.no_grad():
         # 4x4 algebra on the host in fp32 (LAPACK), like the per-scene geometry
         # block: bit-identical to the CPU reference; cuSOLVER's batched inverse
@@ -47,7 +49,7 @@ def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.
         hom = G.homography_params(src_proj.detach().float().cpu(),
                                   ref_proj.detach().float().cpu()).to(src_fea.device)
     feat = ops.pack_features(src_fea, src_fea.dtype if src_fea.dtype == torch.bfloat16 else torch.float32)
-    return ops.homo_warp(feat, hom, depth_values.to(src_fea.device).float(),
+    return ops.homo_warp(feat, hom, depth_values.to(src_fea.device).float().contiguous(),
                          out_dtype=torch.float32)
 
 
@@ -100,3 +102,36 @@ def backproject_Weigh(features, points, projection, depth, voxel_size, prob, gt_
         volume.unflatten(2, (nx, ny, nz))
     valid = valid.view(v, 1, nx, ny, nz)
     return volume, valid, torch.tensor(1.), torch.tensor(1.)
+
+
+def _feature_intrinsics_device(img_meta, stride, device):
+    import numpy as np
+    intr = np.asarray(img_meta["lidar2img"]["intrinsic"], dtype=np.float32).copy()
+    intr[..., :2, :] /= np.float32(img_meta["ori_shape"][0] / (img_meta["img_shape"][0] / stride))
+    return torch.from_numpy(intr).to(device)
+
+
+def compute_depth_scale(height, width, device, img_meta, stride, num_src):
+    """MVSDet.compute_depth_scale (mvsdet.py:1158-1187): shared intrinsics -> (1, num_src, h*w, 1)."""
+    k = _feature_intrinsics_device(img_meta, stride, device)
+    if k.dim() != 2:
+        raise ValueError("compute_depth_scale takes one shared 4x4 intrinsic; use compute_depth_scale_MultiIntrin")
+    scale = ops.ray_depth_scale(k, 1, height, width)                  # identical for every view
+    return scale.reshape(1, 1, height * width, 1).repeat(1, num_src, 1, 1)
+
+
+def compute_depth_scale_MultiIntrin(height, width, device, img_meta, stride, num_src):
+    """MVSDet.compute_depth_scale_MultiIntrin (mvsdet.py:1189-1218): one intrinsic per view
+    (``num_src`` is overridden by the list length, as in the reference)."""
+    k = _feature_intrinsics_device(img_meta, stride, device)
+    if k.dim() != 3:
+        raise ValueError("compute_depth_scale_MultiIntrin takes a list of per-view 4x4 intrinsics")
+    scale = ops.ray_depth_scale(k, k.shape[0], height, width)
+    return scale.reshape(1, k.shape[0], height * width, 1)
+
+
+def process_rgb_raw(orig_rgb, ratio, height, width, src_id):
+    """MVSDet.process_rgb_raw (mvsdet.py:319-333): (n_src,3,H,W) -> (1, num_nei, height*width, 3)."""
+    if ratio != 4:
+        raise ValueError("process_rgb_raw: the reference asserts ratio == 4 (mvsdet.py:326)")
+    return ops.rgb_downsample4(orig_rgb, src_id, height, width)

@@ -1,12 +1,24 @@
-"""Per-scene camera geometry of the MVSDet hot path, evaluated on the host.
+"""Per-scene camera geometry of the MVSDet hot path.
 
 The reference receives the camera matrices as numpy arrays inside ``img_meta``
-and rebuilds small tensors from them every iteration
+and rebuilds small tensors from them every iteration with ~35 tiny ATen calls
+and a Python loop over the views
 (projects/NeRF-Det/nerfdet/mvsdet.py:407-434, :448-450, :1124-1156, :1316-1327).
-All of it is O(V) 4x4 algebra; here it stays on the host in fp32 with the same
-ATen ops (``torch.inverse``, ``matmul``, ``topk``), is packed into ONE pinned
-buffer and uploaded with a single async copy -- the kernels then read a small
-parameter block.  Same names and argument meaning as the reference.
+
+``scene_geometry`` has two prologues producing the same parameter block:
+
+* ``prologue="device"`` (default on CUDA): the host computes only what has to be
+  ATen's bits -- ``ref_proj = K_feat @ w2c`` and ``inverse(ref_proj)``, because the
+  variance volume is sensitive to the rounding of that fp32 inverse
+  -- with a handful of numpy ops and ONE ``torch.inverse``; one pinned upload, then
+  ONE kernel (``mvsd_scene_setup``, csrc/scene_setup.cu) derives neighbour ids,
+  homographies and voxel projections on the device;
+* ``prologue="host"``: everything on the host in fp32 with the reference's own ATen
+  ops (``torch.inverse``, ``matmul``, ``topk``), packed into one pinned upload.  Used
+  where the host needs the neighbour ids (view-sharded halo packing) and as the
+  cross-check of the device prologue (tests/test_gpu_geometry.py: bit-identical).
+
+Same names and argument meaning as the reference for the mirrored functions.
 """
 from __future__ import annotations
 
@@ -18,7 +30,7 @@ import torch
 
 __all__ = ["knn", "get_nearest_pose_ids", "collect_proj", "homography_params",
            "compute_projection", "get_points", "feature_intrinsics", "depth_values_for",
-           "SceneGeometry", "scene_geometry"]
+           "SceneGeometry", "scene_geometry", "host_camera_block"]
 
 
 def knn(x: torch.Tensor, ref: torch.Tensor, k: int, maskself: bool = False) -> torch.Tensor:
@@ -148,6 +160,32 @@ def depth_values_for(near_far_range: Sequence[float], num_depth: int) -> np.ndar
     return dv
 
 
+def host_camera_block(img_meta: dict, stride: int):
+    """The host side of the device prologue: numpy fp32 (w2c [V,4,4], k_feat [4,4] | [V,4,4],
+    ref_proj [V,4,4], inv_ref [V,4,4]).
+
+    ``k_feat`` rows 0-1 are the image intrinsics divided by ``ratio`` in fp32 (what
+    ``tensor[:2] /= python_float`` does, mvsdet.py:422-428).  ``ref_proj = K_feat @ w2c`` is ATen's
+    batched small-matrix product: ``((a0*b0 + a1*b1) + a2*b2) + a3*b3`` with every product and sum
+    rounded to fp32 (no FMA) -- reproduced with numpy fp32 ops, bit for bit
+    (tests/test_geometry_cpu.py); its inverse is ATen's own ``torch.inverse`` (LAPACK)."""
+    w2c = np.asarray(img_meta["lidar2img"]["extrinsic"], dtype=np.float32)
+    if w2c.ndim != 3 or w2c.shape[1:] != (4, 4):
+        raise ValueError("img_meta['lidar2img']['extrinsic'] must be V matrices of 4x4")
+    intr = np.asarray(img_meta["lidar2img"]["intrinsic"], dtype=np.float32)
+    if intr.shape not in ((4, 4), (w2c.shape[0], 4, 4)):
+        raise ValueError("img_meta['lidar2img']['intrinsic'] must be 4x4 or V matrices of 4x4")
+    ratio = np.float32(img_meta["ori_shape"][0] / (img_meta["img_shape"][0] / stride))
+    k_feat = intr.copy()
+    k_feat[..., :2, :] /= ratio
+    a = k_feat if k_feat.ndim == 3 else k_feat[None]
+    ref_proj = a[:, :, 0:1] * w2c[:, 0:1, :]
+    for kk in (1, 2, 3):
+        ref_proj = ref_proj + a[:, :, kk:kk + 1] * w2c[:, kk:kk + 1, :]
+    inv_ref = torch.inverse(torch.from_numpy(ref_proj)).numpy()
+    return w2c, k_feat, ref_proj, inv_ref
+
+
 @dataclass
 class SceneGeometry:
     """Device-resident parameter block of one scene."""
@@ -156,19 +194,68 @@ class SceneGeometry:
     depth_values: torch.Tensor     # [V,D] fp32
     projection: torch.Tensor       # [V,3,4] fp32
     points: torch.Tensor           # [3,nx,ny,nz] fp32
-    neighbor_ids_host: torch.Tensor  # [V,k] int64 (reference dtype)
+    neighbor_ids_host: Optional[torch.Tensor]  # [V,k] int64 (reference dtype); None after the device prologue
     height: int                    # un-padded feature rows (img_shape[0] // stride)
     width: int
     k: int
+    k_feat: Optional[torch.Tensor] = None      # [4,4] | [V,4,4] feature-level intrinsics on the device
+    n_views: int = 0               # views of the scene (the ids in neighbor_ids index these)
+
+    def neighbor_ids_ref(self) -> torch.Tensor:
+        """[V,k] int64 on the host, the reference's dtype (synchronises after the device prologue)."""
+        if self.neighbor_ids_host is None:
+            self.neighbor_ids_host = self.neighbor_ids.cpu().to(torch.int64)
+        return self.neighbor_ids_host
+
+
+def _scene_geometry_device(img_meta: dict, *, stride: int, near_far_range, num_depth: int, n_voxels,
+                           voxel_size, num_neighbors: int, dev: torch.device,
+                           view_slice: Optional[slice]) -> SceneGeometry:
+    from . import ops
+    w2c, k_feat, ref_proj, inv_ref = host_camera_block(img_meta, stride)
+    v_all = w2c.shape[0]
+    k = min(num_neighbors, v_all - 1)
+    begin, end, step = (view_slice or slice(None)).indices(v_all)
+    if step != 1 or end <= begin:
+        raise ValueError("view_slice must be a non-empty contiguous range of reference views")
+    sizes = (w2c.size, k_feat.size, ref_proj.size, inv_ref.size)
+    staging = torch.empty(sum(sizes), dtype=torch.float32, pin_memory=True)
+    host = staging.numpy()
+    o = np.cumsum((0,) + sizes)
+    for i, arr in enumerate((w2c, k_feat, ref_proj, inv_ref)):
+        host[o[i]:o[i + 1]] = arr.reshape(-1)
+    blob = staging.to(dev, non_blocking=True)
+    d_w2c = blob[o[0]:o[1]].view(v_all, 4, 4)
+    d_k = blob[o[1]:o[2]].view(k_feat.shape)
+    nbr, hom, projection = ops.scene_setup(d_w2c, d_k, blob[o[2]:o[3]].view(v_all, 4, 4),
+                                           blob[o[3]:o[4]].view(v_all, 4, 4), k, begin, end - begin)
+    points, dplanes = static_geometry(n_voxels, voxel_size, img_meta["lidar2img"]["origin"],
+                                      near_far_range, num_depth, end - begin, dev)
+    return SceneGeometry(neighbor_ids=nbr, hom=hom, depth_values=dplanes, projection=projection,
+                         points=points, neighbor_ids_host=None,
+                         height=img_meta["img_shape"][0] // stride,
+                         width=img_meta["img_shape"][1] // stride, k=k,
+                         k_feat=d_k if d_k.dim() == 2 else d_k[begin:end], n_views=v_all)
 
 
 def scene_geometry(img_meta: dict, *, stride: int, near_far_range, num_depth: int, n_voxels,
                    voxel_size, num_neighbors: int = 2, device="cuda",
-                   view_slice: Optional[slice] = None) -> SceneGeometry:
-    """Everything mvsdet.py:407-450 derives from ``img_meta``, packed and uploaded
-    with one pinned async copy.  ``view_slice`` restricts the *reference* views
-    (rows of every per-view array) for view-sharded multi-GPU runs; neighbour
-    ids keep indexing the full feature tensor."""
+                   view_slice: Optional[slice] = None, prologue: Optional[str] = None) -> SceneGeometry:
+    """Everything mvsdet.py:407-450 derives from ``img_meta`` as one device-resident parameter
+    block.  ``view_slice`` restricts the *reference* views (rows of every per-view array) for
+    view-sharded multi-GPU runs; neighbour ids keep indexing the full feature tensor.
+    ``prologue``: "device" (default on CUDA) or "host", see the module docstring."""
+    if prologue is None:
+        prologue = "device" if torch.device(device).type == "cuda" else "host"
+    if prologue not in ("device", "host"):
+        raise ValueError("prologue must be 'device' or 'host'")
+    if prologue == "device":
+        if torch.device(device).type != "cuda":
+            raise ValueError("the device prologue needs a CUDA device: mvsdet_b200 has no CPU kernels")
+        return _scene_geometry_device(img_meta, stride=stride, near_far_range=near_far_range,
+                                      num_depth=num_depth, n_voxels=n_voxels, voxel_size=voxel_size,
+                                      num_neighbors=num_neighbors, dev=torch.device(device),
+                                      view_slice=view_slice)
     extr = img_meta["lidar2img"]["extrinsic"]
     w2c = torch.as_tensor(np.array(extr), dtype=torch.float32)
     v_all = w2c.shape[0]
@@ -195,8 +282,9 @@ def scene_geometry(img_meta: dict, *, stride: int, near_far_range, num_depth: in
     points, dplanes = static_geometry(n_voxels, voxel_size, img_meta["lidar2img"]["origin"],
                                       near_far_range, num_depth, v, dev)
 
+    k_rows = k_feat if k_feat.dim() == 2 else (k_feat[view_slice] if view_slice is not None else k_feat)
     parts = [nbr.to(torch.int32).reshape(-1).view(torch.float32) if nbr.numel() else torch.zeros(0),
-             hom.reshape(-1), projection.reshape(-1)]
+             hom.reshape(-1), projection.reshape(-1), k_rows.reshape(-1)]
     sizes = [p.numel() for p in parts]
     if dev.type == "cuda":
         staging = torch.empty(sum(sizes), dtype=torch.float32, pin_memory=True)
@@ -214,4 +302,4 @@ def scene_geometry(img_meta: dict, *, stride: int, near_far_range, num_depth: in
         neighbor_ids_host=nbr,
         height=img_meta["img_shape"][0] // stride,
         width=img_meta["img_shape"][1] // stride,
-        k=k)
+        k=k, k_feat=blob[o[3]:o[4]].view(k_rows.shape), n_views=v_all)

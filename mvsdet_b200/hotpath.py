@@ -56,28 +56,37 @@ class MVSDetHotPath(nn.Module):
         # the autograd.Function layer -- same launchers, same kernels, traceable with fake tensors
         self.dispatcher_ops = bool(dispatcher_ops)
 
-    def geometry(self, img_meta: dict, device, view_slice=None) -> SceneGeometry:
+    def geometry(self, img_meta: dict, device, view_slice=None, prologue=None) -> SceneGeometry:
+        """Per-scene parameter block (mvsdet.py:407-450).  ``prologue``: "device" (default: two
+        host ATen calls + one setup kernel) or "host" (the reference's own ops on the host)."""
         return scene_geometry(img_meta, stride=self.stride, near_far_range=self.near_far_range,
                               num_depth=self.num_depth, n_voxels=self.n_voxels,
                               voxel_size=self.voxel_size, num_neighbors=self.num_neighbors,
-                              device=device, view_slice=view_slice)
+                              device=device, view_slice=view_slice, prologue=prologue)
 
     # -- stages ------------------------------------------------------------
-    def variance(self, feat_cl: torch.Tensor, geo: SceneGeometry, ref_begin: int = 0) -> torch.Tensor:
+    def variance(self, feat_cl: torch.Tensor, geo: SceneGeometry, ref_begin: int = 0,
+                 grad_sink=None) -> torch.Tensor:
         if self.dispatcher_ops:
             if self.variance_dtype not in (torch.float32, torch.bfloat16):
                 raise ValueError("variance_dtype must be float32 or bfloat16")
             return library.plane_sweep_variance(feat_cl, geo.neighbor_ids, geo.hom, geo.depth_values,
                                                 self.variance_dtype == torch.bfloat16, ref_begin)
         return ops.plane_sweep_variance(feat_cl, geo.neighbor_ids, geo.hom, geo.depth_values,
-                                        out_dtype=self.variance_dtype, ref_begin=ref_begin)
+                                        out_dtype=self.variance_dtype, ref_begin=ref_begin,
+                                        grad_sink=grad_sink)
 
-    def hypotheses(self, cost_out: torch.Tensor):
+    def hypotheses(self, cost_out: torch.Tensor, k_feat: Optional[torch.Tensor] = None):
+        """(prob_volume, off_pred, est_depth, est_densities, est_idx, depth_coding); with the
+        feature-level intrinsics ``k_feat`` also the NVS-branch outputs (opacity, depth_scale,
+        est_ray_depth, ray_depth_coding) from the same kernel (mvsdet.py:494, :579, :583)."""
+        if k_feat is not None:
+            return ops.depth_topk_nvs(cost_out, self.near_far_range[0], self.depth_interval, self.topk, k_feat)
         if self.dispatcher_ops:
             return library.depth_topk(cost_out, self.near_far_range[0], self.depth_interval, self.topk)
         return ops.depth_topk(cost_out, self.near_far_range[0], self.depth_interval, self.topk)
 
-    def voxels(self, feat_cl, geo: SceneGeometry, est_depth, est_dens, mode: str = "mean"):
+    def voxels(self, feat_cl, geo: SceneGeometry, est_depth, est_dens, mode: str = "mean", grad_sink=None):
         if self.dispatcher_ops:
             return library.backproject_aggregate(feat_cl, geo.points, geo.projection, est_depth, est_dens,
                                                  self.voxel_size[2], geo.height, geo.width,
@@ -85,35 +94,51 @@ class MVSDetHotPath(nn.Module):
                                                  self.channels_first_volume)
         return ops.backproject_aggregate(feat_cl, geo.points, geo.projection, est_depth, est_dens,
                                          self.voxel_size[2], geo.height, geo.width, mode=mode,
-                                         channels_first=self.channels_first_volume)
+                                         channels_first=self.channels_first_volume, grad_sink=grad_sink)
 
     # -- the whole block ---------------------------------------------------
     def forward(self, feature: torch.Tensor, img_meta: dict,
                 cost_regularization: Optional[Callable] = None,
-                geometry: Optional[SceneGeometry] = None) -> Dict[str, torch.Tensor]:
+                geometry: Optional[SceneGeometry] = None, nvs: bool = False) -> Dict[str, torch.Tensor]:
         """feature [V,C,Hf,Wf] (fp32 NCHW as the reference's FPN gives it, or
         already channels_last / bf16).  Returns a dict with
           volume_mean [C,nx,ny,nz], valid [1,nx,ny,nz] (float count, as
           extract_feat returns it, mvsdet.py:698), count int32 [N],
           variance, prob_volume, off_pred, est_depth, est_densities, est_idx, opacity,
-          depth_coding [V,1,h,w] -- the reference's intermediates."""
+          depth_coding [V,1,h,w] -- the reference's intermediates; ``nvs=True`` adds
+          depth_scale [V,h*w,1], est_ray_depth [V,h*w,1,T] and ray_depth_coding [V,h*w,1]
+          in the reference's layouts (mvsdet.py:488-494, :583), from the top-k kernel."""
         cost_net = cost_regularization or self.cost_regularization
         if cost_net is None:
             raise ValueError("a cost_regularization callable is required (mvsdet.py:470)")
         geo = geometry or self.geometry(img_meta, feature.device)
-        feat_cl = ops.pack_features(feature, self.feature_dtype)
-        variance = self.variance(feat_cl, geo)
+        # one fp32 gradient accumulator shared by the two consumers of the packed features
+        # (ops.FeatureGradSink); the torch.library route keeps plain functional autograd
+        feat_cl, sink = ops.pack_features(feature, self.feature_dtype, sink=True)
+        if self.dispatcher_ops:
+            sink = None
+        variance = self.variance(feat_cl, geo, grad_sink=sink)
         cost_out = cost_net(variance)
-        prob, off, est_depth, est_dens, est_idx, coding = self.hypotheses(cost_out)
-        vol, count = self.voxels(feat_cl, geo, est_depth, est_dens)
+        hyp = self.hypotheses(cost_out, geo.k_feat if nvs else None)
+        prob, off, est_depth, est_dens, est_idx, coding = hyp[:6]
+        vol, count = self.voxels(feat_cl, geo, est_depth, est_dens, grad_sink=sink)
         nx, ny, nz = self.n_voxels
         c = feat_cl.shape[1]
         volume_mean = vol.view(c, nx, ny, nz) if vol.is_contiguous() else vol.unflatten(1, (nx, ny, nz))
-        return dict(volume_mean=volume_mean, valid=count.view(1, nx, ny, nz).float(), count=count,
-                    variance=variance, prob_volume=prob, off_pred=off, est_depth=est_depth,
-                    est_densities=est_dens, est_idx=est_idx,
-                    # NVS branch: opacity = max_d prob_volume (mvsdet.py:579) is the top-1
-                    # hypothesis probability, bit for bit
-                    opacity=est_dens[:, 0],
-                    depth_coding=coding[:, :geo.height, :geo.width].unsqueeze(1),
-                    neighbor_ids=geo.neighbor_ids_host)
+        out = dict(volume_mean=volume_mean, valid=count.view(1, nx, ny, nz).float(), count=count,
+                   variance=variance, prob_volume=prob, off_pred=off, est_depth=est_depth,
+                   est_densities=est_dens, est_idx=est_idx,
+                   # NVS branch: opacity = max_d prob_volume (mvsdet.py:579) is the top-1
+                   # hypothesis probability, bit for bit
+                   opacity=est_dens[:, 0],
+                   depth_coding=coding[:, :geo.height, :geo.width].unsqueeze(1),
+                   # int32 on the device (device prologue); .long() gives the reference's dtype
+                   neighbor_ids=geo.neighbor_ids)
+        if nvs:
+            v, h, w = est_depth.shape[0], geo.height, geo.width
+            opacity, scale, ray_depth, ray_coding = hyp[6:]
+            out["opacity"] = opacity
+            out["depth_scale"] = scale[:, :h, :w].reshape(v, h * w, 1)
+            out["est_ray_depth"] = ray_depth[:, :, :h, :w].reshape(v, self.topk, h * w).transpose(2, 1).unsqueeze(2)
+            out["ray_depth_coding"] = ray_coding[:, :h, :w].reshape(v, h * w, 1)
+        return out

@@ -21,8 +21,9 @@ import torch
 from . import _lib
 from ._lib import (BF16, BP_MEAN, BP_PER_VIEW, BP_SUM, CHANNELS_FIRST, CHANNELS_LAST, F32)
 
-__all__ = ["pack_features", "plane_sweep_variance", "homo_warp", "depth_topk", "topk_hypotheses",
-           "backproject_aggregate", "backproject_per_view", "voxel_normalize"]
+__all__ = ["pack_features", "plane_sweep_variance", "homo_warp", "depth_topk", "depth_topk_nvs",
+           "topk_hypotheses", "ray_depth_scale", "rgb_downsample4", "backproject_aggregate",
+           "backproject_per_view", "voxel_normalize", "scene_setup"]
 
 
 # --------------------------------------------------------------------------
@@ -71,15 +72,82 @@ def _empty_ndhwc(v, c, d, h, w, dtype, device) -> torch.Tensor:
     return torch.empty((v, d, h, w, c), dtype=dtype, device=device).permute(0, 4, 1, 2, 3)
 
 
+# Re-layouts of a volume-sized gradient are a hidden 1.2 GB transpose per scene: they are counted so a
+# caller (and tests/test_gpu_costreg.py, with the real CostRegNet_3DGS attached) can assert that the
+# upstream gradient arrives in channels_last_3d and that no copy fires.
+relayout_count = {"g_variance": 0, "g_variance_cast": 0}
+
+
 def _as_ndhwc(t: torch.Tensor, dtype=None) -> torch.Tensor:
     if dtype is not None and t.dtype != dtype:
+        relayout_count["g_variance_cast"] += 1
         t = t.to(dtype)
-    return t if _is_ndhwc(t) else t.contiguous(memory_format=torch.channels_last_3d)
+    if _is_ndhwc(t):
+        return t
+    relayout_count["g_variance"] += 1
+    return t.contiguous(memory_format=torch.channels_last_3d)
 
 
 # --------------------------------------------------------------------------
 # layout: [V,C,H,W] fp32 contiguous <-> channels-last
 # --------------------------------------------------------------------------
+class FeatureGradSink:
+    """One fp32 channels-last gradient accumulator shared by every consumer of a packed feature
+    tensor (the training-step form ``ScenePipeline`` uses, expressed in autograd).
+
+    Without it each backward node allocates and zero-fills its own 98 MB accumulator, the engine
+    casts every partial gradient to the packed tensor's dtype (bf16: 2^-9 relative rounding),
+    adds the partials, and the pack node converts back to fp32 before the transpose.  With a sink
+    the plane-sweep and back-projection backward kernels RED into ONE accumulator in fp32, return
+    no gradient for the packed tensor, and ``pack_features``' backward transposes the accumulator
+    to the FPN's fp32 NCHW layout once: fp32 accumulation end to end, ~0.5 GB less traffic per
+    scene.  Created by ``pack_features(x, dtype, sink=True)``; an implementation detail of
+    ``MVSDetHotPath.forward``."""
+
+    def __init__(self, shape, device):
+        self.shape = tuple(shape)          # logical [V,C,H,W]
+        self.device = device
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self) -> torch.Tensor:
+        """the accumulator (logical [V,C,H,W], channels-last memory), zero-filled on first use"""
+        if self.buf is None:
+            v, c, h, w = self.shape
+            self.buf = _zeros_nhwc(v, c, h, w, torch.float32, self.device)
+        return self.buf
+
+    def take(self) -> Optional[torch.Tensor]:
+        buf, self.buf = self.buf, None
+        return buf
+
+
+class _PackFeaturesSink(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, dtype: torch.dtype, sink: FeatureGradSink):
+        v, c, h, w = x.shape
+        out = _empty_nhwc(v, c, h, w, dtype, x.device)
+        _lib.call("mvsd_pack_nchw_to_nhwc", x.data_ptr(), out.data_ptr(), _code(dtype),
+                  v, c, h, w, _stream())
+        ctx.sink = sink
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        acc = ctx.sink.take()
+        if g is not None:                   # a consumer that does not know the sink
+            g = g.float()
+            acc = g if acc is None else acc.add_(g)
+        if acc is None:
+            return None, None, None
+        v, c, h, w = acc.shape
+        if not _is_nhwc(acc):
+            acc = acc.contiguous(memory_format=torch.channels_last)
+        out = torch.empty((v, c, h, w), dtype=torch.float32, device=acc.device)
+        _lib.call("mvsd_unpack_nhwc_to_nchw", acc.data_ptr(), out.data_ptr(), 0, v, c, h, w, _stream())
+        return out, None, None
+
+
 class _PackFeatures(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: torch.Tensor, dtype: torch.dtype):
@@ -99,19 +167,28 @@ class _PackFeatures(torch.autograd.Function):
         return out, None
 
 
-def pack_features(x: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+def pack_features(x: torch.Tensor, dtype: torch.dtype = torch.float32, sink: bool = False):
     """[V,C,H,W] features -> the same logical tensor in channels_last memory
     format and ``dtype`` (fp32 or bf16).  A tensor that already has that layout
     and dtype is returned as is; an fp32 NCHW-contiguous tensor (the reference's
-    FPN output, mvsdet.py:373-376) goes through the transpose kernel."""
+    FPN output, mvsdet.py:373-376) goes through the transpose kernel.
+
+    ``sink=True`` returns ``(packed, FeatureGradSink | None)``: when ``x`` needs a gradient and goes
+    through the transpose kernel, the sink collects the fp32 gradients of the consumers that are
+    given it (``plane_sweep_variance(..., grad_sink=)``, ``backproject_aggregate(..., grad_sink=)``)."""
     _need_cuda("features", x)
     if x.dim() != 4:
         raise ValueError("features must be [V,C,H,W]")
     if _is_nhwc(x) and x.shape[1] > 1:
-        return x if x.dtype == dtype else x.to(dtype)
+        out = x if x.dtype == dtype else x.to(dtype)
+        return (out, None) if sink else out
     if x.dtype != torch.float32 or not x.is_contiguous():
         x = x.float().contiguous()
-    return _PackFeatures.apply(x, dtype)
+    if sink and x.requires_grad and torch.is_grad_enabled():
+        gs = FeatureGradSink(x.shape, x.device)
+        return _PackFeaturesSink.apply(x, dtype, gs), gs
+    out = _PackFeatures.apply(x, dtype)
+    return (out, None) if sink else out
 
 
 # --------------------------------------------------------------------------
@@ -126,45 +203,50 @@ def _sweep_fwd_raw(feat, nbr_ids, hom, depth_values, out_dtype, ref_begin):
     out = _empty_ndhwc(v, c, d, h, w, out_dtype, feat.device)
     _lib.call("mvsd_plane_sweep_fwd", feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids),
               _ptr(hom), depth_values.data_ptr(), out.data_ptr(), _code(out_dtype),
-              CHANNELS_LAST, v, c, d, h, w, k, ref_begin, _stream())
+              CHANNELS_LAST, v, c, d, h, w, k, ref_begin, feat.shape[0], _stream())
     return out
 
 
-def _sweep_bwd_raw(g, feat, nbr_ids, hom, depth_values, ref_begin):
-    """enqueue mvsd_plane_sweep_bwd; -> dL/dfeat in feat's dtype, channels_last"""
+def _sweep_bwd_raw(g, feat, nbr_ids, hom, depth_values, ref_begin, acc=None):
+    """enqueue mvsd_plane_sweep_bwd; -> dL/dfeat in feat's dtype, channels_last.  ``acc``: an
+    fp32 channels-last accumulator to RED into instead (FeatureGradSink); returns None then."""
     vf, c, h, w = feat.shape
     v = nbr_ids.shape[0]
     d = depth_values.shape[1]
     k = nbr_ids.shape[1]
     gdt = torch.bfloat16 if (g.dtype == torch.bfloat16 and feat.dtype == torch.bfloat16) else torch.float32
     g = _as_ndhwc(g, gdt)
-    g_feat = _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
+    g_feat = acc if acc is not None else _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
     _lib.call("mvsd_plane_sweep_bwd", g.data_ptr(), _code(g.dtype), CHANNELS_LAST,
               feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids), _ptr(hom),
-              depth_values.data_ptr(), g_feat.data_ptr(), v, c, d, h, w, k, ref_begin,
+              depth_values.data_ptr(), g_feat.data_ptr(), v, c, d, h, w, k, ref_begin, vf,
               _stream())
+    if acc is not None:
+        return None
     return g_feat.to(feat.dtype) if feat.dtype != torch.float32 else g_feat
 
 
 class _PlaneSweepVariance(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, nbr_ids, hom, depth_values, out_dtype, ref_begin):
+    def forward(ctx, feat, nbr_ids, hom, depth_values, out_dtype, ref_begin, sink=None):
         out = _sweep_fwd_raw(feat, nbr_ids, hom, depth_values, out_dtype, ref_begin)
         ctx.save_for_backward(feat, nbr_ids, hom, depth_values)
         ctx.ref_begin = ref_begin
+        ctx.sink = sink
         return out
 
     @staticmethod
     def backward(ctx, g):
         feat, nbr_ids, hom, depth_values = ctx.saved_tensors
-        g_feat = _sweep_bwd_raw(g, feat, nbr_ids, hom, depth_values, ctx.ref_begin)
-        return g_feat, None, None, None, None, None
+        acc = ctx.sink.get() if ctx.sink is not None else None
+        g_feat = _sweep_bwd_raw(g, feat, nbr_ids, hom, depth_values, ctx.ref_begin, acc)
+        return g_feat, None, None, None, None, None, None
 
 
 def plane_sweep_variance(feat: torch.Tensor, nbr_ids: torch.Tensor, hom: torch.Tensor,
                          depth_values: torch.Tensor,
                          out_dtype: torch.dtype = torch.float32,
-                         ref_begin: int = 0) -> torch.Tensor:
+                         ref_begin: int = 0, grad_sink: Optional[FeatureGradSink] = None) -> torch.Tensor:
     """Fused mvsdet.py:439-467: channels-last features [Vf,C,H,W] (fp32/bf16),
     neighbour ids [V,k] int32 (indices into feat), homographies [V,k,12], depth
     planes [V,D] -> variance volume, logical [V,C,D,H,W] in channels_last_3d.
@@ -183,8 +265,10 @@ def plane_sweep_variance(feat: torch.Tensor, nbr_ids: torch.Tensor, hom: torch.T
         raise ValueError("reference views [ref_begin, ref_begin+V) exceed feat")
     if hom.dtype != torch.float32 or depth_values.dtype != torch.float32:
         raise ValueError("hom and depth_values must be float32")
+    if grad_sink is not None and grad_sink.shape != tuple(feat.shape):
+        raise ValueError("grad_sink belongs to a different feature tensor")
     return _PlaneSweepVariance.apply(feat, nbr_ids, hom.contiguous(), depth_values.contiguous(),
-                                     out_dtype, int(ref_begin))
+                                     out_dtype, int(ref_begin), grad_sink)
 
 
 class _HomoWarp(torch.autograd.Function):
@@ -195,7 +279,7 @@ class _HomoWarp(torch.autograd.Function):
         out = _empty_ndhwc(b, c, d, h, w, out_dtype, src.device)
         _lib.call("mvsd_homo_warp_fwd", src.data_ptr(), _code(src.dtype), hom.data_ptr(),
                   depth_values.data_ptr(), out.data_ptr(), _code(out_dtype), CHANNELS_LAST,
-                  b, c, d, h, w, _stream())
+                  b, c, d, h, w, int(depth_values.dim() == 4), _stream())
         ctx.save_for_backward(hom, depth_values)
         ctx.src_meta = (src.shape, src.dtype)
         return out
@@ -208,18 +292,23 @@ class _HomoWarp(torch.autograd.Function):
         g = _as_ndhwc(g, torch.float32 if g.dtype != torch.bfloat16 else torch.bfloat16)
         g_src = _zeros_nhwc(b, c, h, w, torch.float32, g.device)
         _lib.call("mvsd_homo_warp_bwd", g.data_ptr(), _code(g.dtype), CHANNELS_LAST, hom.data_ptr(),
-                  depth_values.data_ptr(), g_src.data_ptr(), b, c, d, h, w, _stream())
+                  depth_values.data_ptr(), g_src.data_ptr(), b, c, d, h, w,
+                  int(depth_values.dim() == 4), _stream())
         return (g_src if sdtype == torch.float32 else g_src.to(sdtype)), None, None, None
 
 
 def homo_warp(src: torch.Tensor, hom: torch.Tensor, depth_values: torch.Tensor,
               out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """mvs_models/module.py:105-146 with the homography already reduced to
-    [B,12] (rot rows, trans): channels-last [B,C,H,W] -> [B,C,D,H,W]."""
+    [B,12] (rot rows, trans): channels-last [B,C,H,W] -> [B,C,D,H,W].
+    ``depth_values`` is [B,D] or the per-pixel form [B,D,H,W] (module.py:130-133)."""
     for n, t in (("src", src), ("hom", hom), ("depth_values", depth_values)):
         _need_cuda(n, t)
     if not _is_nhwc(src):
         raise ValueError("src must be channels_last; use ops.pack_features")
+    if depth_values.dim() not in (2, 4) or depth_values.shape[0] != src.shape[0] or \
+            (depth_values.dim() == 4 and tuple(depth_values.shape[2:]) != tuple(src.shape[2:])):
+        raise ValueError("depth_values must be [B,D] or [B,D,H,W]")
     return _HomoWarp.apply(src, hom.contiguous().float(), depth_values.contiguous().float(), out_dtype)
 
 
@@ -238,8 +327,22 @@ def _cost_strides(cost_out: torch.Tensor):
     return cost_out, sv, sc, sd, sw
 
 
-def _topk_fwd_raw(cost_out, near, interval, topk, raw):
-    """enqueue mvsd_depth_topk_fwd; -> (cost_out as the kernel read it, the six outputs)"""
+def _ray_intr(ray_intr, v):
+    """[4,4] or [V,4,4] fp32 feature-level intrinsics -> (tensor, per_view flag)"""
+    if ray_intr is None:
+        return None, 0
+    _need_cuda("ray_intrinsics", ray_intr)
+    k = ray_intr.float().contiguous()
+    if tuple(k.shape) == (4, 4):
+        return k, 0
+    if tuple(k.shape) == (v, 4, 4):
+        return k, 1
+    raise ValueError(f"ray intrinsics must be [4,4] or [{v},4,4], got {tuple(ray_intr.shape)}")
+
+
+def _topk_fwd_raw(cost_out, near, interval, topk, raw, ray_intr=None):
+    """enqueue mvsd_depth_topk_fwd; -> (cost_out as the kernel read it, the six outputs, and with
+    ``ray_intr`` the four NVS outputs opacity, depth_scale, est_ray_depth, ray_depth_coding)"""
     cost_out, sv, sc, sd, sp = _cost_strides(cost_out)
     v, _, d, h, w = cost_out.shape
     dev = cost_out.device
@@ -250,24 +353,33 @@ def _topk_fwd_raw(cost_out, near, interval, topk, raw):
     est_dens = torch.empty((v, topk, h, w), **f32)
     est_idx = torch.empty((v, topk, h, w), dtype=torch.int64, device=dev)
     coding = torch.empty((v, h, w), **f32)
+    kmat, per_view = _ray_intr(ray_intr, v)
+    nvs = ()
+    if kmat is not None:
+        nvs = (torch.empty((v, h, w), **f32), torch.empty((v, h, w), **f32),
+               torch.empty((v, topk, h, w), **f32), torch.empty((v, h, w), **f32))
     _lib.call("mvsd_depth_topk_fwd", cost_out.data_ptr(), sv, sc, sd, sp, prob.data_ptr(),
               off.data_ptr(), est_depth.data_ptr(), est_dens.data_ptr(), est_idx.data_ptr(),
-              coding.data_ptr(), float(near), float(interval), int(raw), v, d, h, w, topk, _stream())
-    return cost_out, (prob, off, est_depth, est_dens, est_idx, coding)
+              coding.data_ptr(), _ptr(kmat), per_view, *(_ptr(t) for t in (nvs or (None,) * 4)),
+              float(near), float(interval), int(raw), v, d, h, w, topk, _stream())
+    return cost_out, (prob, off, est_depth, est_dens, est_idx, coding) + nvs
 
 
 def _topk_bwd_raw(cost_out, est_idx, g_prob, g_off, g_depth, g_dens, g_coding, near, interval,
-                  topk, raw):
-    """enqueue mvsd_depth_topk_bwd (any of the five upstream gradients may be None)"""
+                  topk, raw, ray_intr=None, g_ray_depth=None, g_ray_coding=None):
+    """enqueue mvsd_depth_topk_bwd (any of the upstream gradients may be None)"""
     cost_out, sv, sc, sd, sp = _cost_strides(cost_out)
     v, _, d, h, w = cost_out.shape
 
     def prep(g):
         return None if g is None else g.contiguous().float()
-    g_prob, g_off, g_depth, g_dens, g_coding = map(prep, (g_prob, g_off, g_depth, g_dens, g_coding))
+    g_prob, g_off, g_depth, g_dens, g_coding, g_ray_depth, g_ray_coding = map(
+        prep, (g_prob, g_off, g_depth, g_dens, g_coding, g_ray_depth, g_ray_coding))
+    kmat, per_view = _ray_intr(ray_intr, v)
     g_cost = torch.empty((v, 2, d, h, w), dtype=torch.float32, device=cost_out.device)
     _lib.call("mvsd_depth_topk_bwd", cost_out.data_ptr(), sv, sc, sd, sp, est_idx.data_ptr(),
               _ptr(g_prob), _ptr(g_off), _ptr(g_depth), _ptr(g_dens), _ptr(g_coding),
+              _ptr(kmat), per_view, _ptr(g_ray_depth), _ptr(g_ray_coding),
               g_cost.data_ptr(), float(near), float(interval), int(raw), v, d, h, w, topk, _stream())
     return g_cost
 
@@ -290,6 +402,31 @@ class _DepthTopk(torch.autograd.Function):
         return g_cost, None, None, None, None
 
 
+class _DepthTopkNVS(torch.autograd.Function):
+    """depth_topk plus the NVS-branch epilogue; opacity is the top-1 density and shares its
+    gradient path, depth_scale is a constant of the intrinsics."""
+
+    @staticmethod
+    def forward(ctx, cost_out, near, interval, topk, ray_intr):
+        cost_out, outs = _topk_fwd_raw(cost_out, near, interval, topk, 0, ray_intr)
+        ctx.save_for_backward(cost_out, outs[4], ray_intr)
+        ctx.consts = (float(near), float(interval), topk)
+        ctx.mark_non_differentiable(outs[4], outs[7])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_prob, g_off, g_depth, g_dens, _g_idx, g_coding, g_opacity, _g_scale,
+                 g_ray_depth, g_ray_coding):
+        cost_out, est_idx, ray_intr = ctx.saved_tensors
+        near, interval, topk = ctx.consts
+        if g_opacity is not None:                      # opacity == est_dens[:, 0]
+            g_dens = torch.zeros_like(est_idx, dtype=torch.float32) if g_dens is None else g_dens.clone()
+            g_dens[:, 0] += g_opacity
+        g_cost = _topk_bwd_raw(cost_out, est_idx, g_prob, g_off, g_depth, g_dens, g_coding,
+                               near, interval, topk, 0, ray_intr, g_ray_depth, g_ray_coding)
+        return g_cost, None, None, None, None
+
+
 def depth_topk(cost_out: torch.Tensor, near: float, interval: float, topk: int):
     """Fused mvsdet.py:470-482 + sample_depth_prob (:266-283) + compute_avg_depth
     (:298-317).  cost_out [V,2,D,H,W] -> (prob_volume [V,D,H,W], off_pred
@@ -299,6 +436,54 @@ def depth_topk(cost_out: torch.Tensor, near: float, interval: float, topk: int):
     if cost_out.dim() != 5 or cost_out.shape[1] != 2:
         raise ValueError("cost_out must be [V,2,D,H,W]")
     return _DepthTopk.apply(cost_out, near, interval, int(topk), 0)
+
+
+def depth_topk_nvs(cost_out: torch.Tensor, near: float, interval: float, topk: int,
+                   k_feat: torch.Tensor):
+    """``depth_topk`` with the NVS-branch consumers computed in the same kernel (SURVEY.md 8f
+    rank 3).  ``k_feat``: feature-level intrinsics [4,4] or [V,4,4].  Returns the six outputs of
+    ``depth_topk`` followed by
+      opacity [V,H,W]           max_d prob_volume                          mvsdet.py:579
+      depth_scale [V,H,W]       compute_depth_scale[_MultiIntrin]          mvsdet.py:1158-1218
+      est_ray_depth [V,T,H,W]   est_depth / (depth_scale + 1e-8)           mvsdet.py:494
+      ray_depth_coding [V,H,W]  depth_coding / (depth_scale + 1e-8)        mvsdet.py:583
+    (full, un-cropped maps; the caller crops / reshapes as it does est_depth)."""
+    _need_cuda("cost_out", cost_out)
+    if cost_out.dim() != 5 or cost_out.shape[1] != 2:
+        raise ValueError("cost_out must be [V,2,D,H,W]")
+    kmat, _ = _ray_intr(k_feat, cost_out.shape[0])
+    return _DepthTopkNVS.apply(cost_out, near, interval, int(topk), kmat)
+
+
+def ray_depth_scale(k_feat: torch.Tensor, n_views: int, height: int, width: int) -> torch.Tensor:
+    """compute_depth_scale / compute_depth_scale_MultiIntrin (mvsdet.py:1158-1218) alone:
+    [4,4] or [V,4,4] feature-level intrinsics -> depth_scale [V,height,width]."""
+    kmat, per_view = _ray_intr(k_feat, n_views)
+    out = torch.empty((n_views, height, width), dtype=torch.float32, device=kmat.device)
+    _lib.call("mvsd_ray_depth_scale", kmat.data_ptr(), per_view, out.data_ptr(), n_views, height,
+              width, _stream())
+    return out
+
+
+def rgb_downsample4(rgb: torch.Tensor, src_ids, height: int, width: int) -> torch.Tensor:
+    """process_rgb_raw (mvsdet.py:319-333) for ratio 4: rgb [V,3,H,W] fp32 -> [1, n, height*width, 3]."""
+    _need_cuda("rgb", rgb)
+    if rgb.dim() != 4 or rgb.shape[1] != 3:
+        raise ValueError("rgb must be [V,3,H,W]")
+    rgb = rgb.float().contiguous()
+    v, _, hh, ww = rgb.shape
+    ids = None
+    n = v
+    if src_ids is not None:
+        ids = torch.as_tensor(src_ids, dtype=torch.int64).reshape(-1)
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= v):
+            raise ValueError("src_id outside the image batch")
+        ids = ids.to(rgb.device)
+        n = ids.numel()
+    out = torch.empty((1, n, height * width, 3), dtype=torch.float32, device=rgb.device)
+    _lib.call("mvsd_rgb_downsample4", rgb.data_ptr(), _ptr(ids), n, out.data_ptr(), v, hh, ww,
+              int(height), int(width), _stream())
+    return out
 
 
 def topk_hypotheses(prob_off: torch.Tensor, near: float, interval: float, topk: int):
@@ -346,25 +531,29 @@ def _bp_fwd_raw(feat, points, projection, est_depth, est_dens, vs_z, h, w, mode,
 
 
 def _bp_bwd_raw(g_out, feat, points, projection, est_depth, est_dens, count, vs_z, h, w, mode,
-                channels_first):
-    """enqueue mvsd_backproject_bwd + mvsd_prob_norm_bwd; -> (dL/dfeat, dL/dest_dens)"""
+                channels_first, acc=None):
+    """enqueue mvsd_backproject_bwd + mvsd_prob_norm_bwd; -> (dL/dfeat, dL/dest_dens); with ``acc``
+    (FeatureGradSink accumulator) the feature gradient is RED-added there and None is returned"""
     v, c, fh, fw = feat.shape
     t = est_depth.shape[1]
     n = points.numel() // 3
     sv, st, sy, sx = est_depth.stride()
     g_out = g_out.float()
     g_mem = g_out.contiguous() if channels_first else g_out.t().contiguous()
-    g_feat = _zeros_nhwc(v, c, fh, fw, torch.float32, feat.device)
+    g_feat = acc if acc is not None else _zeros_nhwc(v, c, fh, fw, torch.float32, feat.device)
     g_pn = _zeros_strided_like(est_dens)
     g_prob = _zeros_strided_like(est_dens)
     _lib.call("mvsd_backproject_bwd", g_mem.data_ptr(),
-              CHANNELS_FIRST if channels_first else CHANNELS_LAST, mode, count.data_ptr(),
+              CHANNELS_FIRST if channels_first else CHANNELS_LAST, mode,
+              count.data_ptr() if mode == BP_MEAN else None,
               feat.data_ptr(), _code(feat.dtype), fh, fw, points.data_ptr(),
               projection.data_ptr(), est_depth.data_ptr(), est_dens.data_ptr(),
               sv, sy, sx, st, float(vs_z), g_feat.data_ptr(), g_pn.data_ptr(),
               v, c, h, w, t, n, _stream())
     _lib.call("mvsd_prob_norm_bwd", est_dens.data_ptr(), g_pn.data_ptr(), g_prob.data_ptr(),
               sv, sy, sx, st, v, h, w, t, _stream())
+    if acc is not None:
+        return None, g_prob
     g_feat = g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)
     return g_feat, g_prob
 
@@ -372,11 +561,16 @@ def _bp_bwd_raw(g_out, feat, points, projection, est_depth, est_dens, count, vs_
 class _BackprojectAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, points, projection, est_depth, est_dens, vs_z, h, w, mode, channels_first,
-                out=None, count=None):
+                out=None, count=None, sink=None):
         res, count = _bp_fwd_raw(feat, points, projection, est_depth, est_dens, vs_z, h, w, mode,
                                  channels_first, out, count)
-        ctx.save_for_backward(feat, points, projection, est_depth, est_dens, count)
+        # Only MEAN mode needs the count in its backward (s_u = 1/(count+1e-8)); SUM mode -- the
+        # only mode that accepts caller-owned (reused, peer-mapped) buffers -- saves nothing that
+        # aliases them, so a later call that overwrites the buffers cannot corrupt this graph.
+        ctx.save_for_backward(feat, points, projection, est_depth, est_dens,
+                              count if mode == BP_MEAN else None)
         ctx.consts = (float(vs_z), h, w, mode, channels_first)
+        ctx.sink = sink
         ctx.mark_non_differentiable(count)
         return res, count
 
@@ -384,9 +578,10 @@ class _BackprojectAggregate(torch.autograd.Function):
     def backward(ctx, g_out, _g_count):
         feat, points, projection, est_depth, est_dens, count = ctx.saved_tensors
         vs_z, h, w, mode, channels_first = ctx.consts
+        acc = ctx.sink.get() if ctx.sink is not None else None
         g_feat, g_prob = _bp_bwd_raw(g_out, feat, points, projection, est_depth, est_dens, count,
-                                     vs_z, h, w, mode, channels_first)
-        return g_feat, None, None, None, g_prob, None, None, None, None, None, None, None
+                                     vs_z, h, w, mode, channels_first, acc)
+        return g_feat, None, None, None, g_prob, None, None, None, None, None, None, None, None
 
 
 def _check_hyp(name, t, v, fh, fw):
@@ -400,7 +595,8 @@ def _check_hyp(name, t, v, fh, fw):
 def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: float,
                           height: int, width: int, *, mode: str = "mean",
                           channels_first: bool = True, out: Optional[torch.Tensor] = None,
-                          count_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                          count_out: Optional[torch.Tensor] = None,
+                          grad_sink: Optional[FeatureGradSink] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused backproject_Weigh (mvsdet.py:1372-1492) + aggregation (:511-515,
     :681-682).
 
@@ -412,7 +608,9 @@ def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: f
     The result is logical [C,N]; with channels_first=False its memory is [N,C]
     (channels_last_3d once viewed as [C,nx,ny,nz]).  ``out`` / ``count_out``: write into
     caller-owned buffers (memory order of the volume: [C,N] or [N,C] contiguous) -- the
-    view-sharded path lets the kernel write its partials straight into peer-mapped memory."""
+    view-sharded path lets the kernel write its partials straight into peer-mapped memory
+    (mode='sum' only; the buffers are overwritten in place without bumping autograd's version
+    counters, so hand the same buffers to a later call only after the result has been consumed)."""
     _need_cuda("feat", feat)
     if not _is_nhwc(feat):
         raise ValueError("feat must be channels_last; use ops.pack_features")
@@ -428,10 +626,15 @@ def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: f
     if height > fh or width > fw:
         raise ValueError("crop exceeds the feature map")
     m = {"mean": BP_MEAN, "sum": BP_SUM}[mode]
+    if grad_sink is not None and grad_sink.shape != tuple(feat.shape):
+        raise ValueError("grad_sink belongs to a different feature tensor")
+    if m == BP_MEAN and (out is not None or count_out is not None):
+        raise ValueError("caller-owned out / count_out buffers are for mode='sum' (the multi-GPU partials): "
+                         "in 'mean' mode the backward reads the count, which a reused buffer would clobber")
     return _BackprojectAggregate.apply(feat, points.contiguous().float(),
                                        projection.contiguous().float(), est_depth, est_dens,
                                        float(vs_z), int(height), int(width), m, bool(channels_first),
-                                       out, count_out)
+                                       out, count_out, grad_sink)
 
 
 class _BackprojectPerView(torch.autograd.Function):
@@ -519,3 +722,31 @@ def voxel_normalize(volume_sum: torch.Tensor, count: torch.Tensor) -> torch.Tens
     _lib.call("mvsd_voxel_normalize", mem.data_ptr(), count.data_ptr(), out.data_ptr(),
               CHANNELS_LAST, c, n, _stream())
     return out.t()
+
+
+# --------------------------------------------------------------------------
+# per-scene camera geometry (device prologue)
+# --------------------------------------------------------------------------
+def scene_setup(w2c: torch.Tensor, k_feat: torch.Tensor, ref_proj: torch.Tensor, inv_ref: torch.Tensor,
+                k: int, ref_begin: int = 0, n_ref: Optional[int] = None):
+    """mvsd_scene_setup: neighbour ids, homographies and projections of one scene in one launch
+    (mvsdet.py:43-104, :249-264, :432-434, :1124-1156; module.py:116-118).  All inputs are DEVICE
+    fp32 tensors: w2c [V,4,4], k_feat [4,4] or [V,4,4] (feature level), ref_proj = K_feat @ w2c and
+    its inverse [V,4,4] (both from the host's ATen calls, see geometry.scene_geometry).
+    -> (nbr_ids [n_ref,k] int32, hom [n_ref,k,12], projection [n_ref,3,4])."""
+    for n, t in (("w2c", w2c), ("k_feat", k_feat), ("ref_proj", ref_proj), ("inv_ref", inv_ref)):
+        _need_cuda(n, t)
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{n} must be contiguous float32")
+    v = w2c.shape[0]
+    n_ref = v - ref_begin if n_ref is None else int(n_ref)
+    per_view = int(k_feat.dim() == 3)
+    dev = w2c.device
+    out = torch.empty(n_ref * k * 13 + n_ref * 12, dtype=torch.float32, device=dev)
+    nbr = out[:n_ref * k].view(torch.int32).view(n_ref, k)
+    hom = out[n_ref * k:n_ref * k * 13].view(n_ref, k, 12)
+    proj = out[n_ref * k * 13:].view(n_ref, 3, 4)
+    _lib.call("mvsd_scene_setup", w2c.data_ptr(), k_feat.data_ptr(), per_view, ref_proj.data_ptr(),
+              inv_ref.data_ptr(), _ptr(nbr) if k else None, _ptr(hom) if k else None, proj.data_ptr(),
+              v, int(k), int(ref_begin), n_ref, _stream())
+    return nbr, hom, proj

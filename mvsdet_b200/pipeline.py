@@ -175,13 +175,14 @@ class ScenePipeline:
         else:
             run("plane_sweep_fwd", "mvsd_plane_sweep_fwd", self.feat_cl.data_ptr(), fdt,
                 geo.neighbor_ids.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(),
-                self.variance.data_ptr(), vdt, CHANNELS_LAST, v, c, d, hf, wf, k, 0, st)
+                self.variance.data_ptr(), vdt, CHANNELS_LAST, v, c, d, hf, wf, k, 0, v, st)
         sc = self.cost_out.stride()
         with torch.cuda.stream(aux):
             sa = aux.cuda_stream
             run("depth_topk_fwd", "mvsd_depth_topk_fwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2],
                 sc[4], self.prob_volume.data_ptr(), self.off_pred.data_ptr(), self.est_depth.data_ptr(),
                 self.est_dens.data_ptr(), self.est_idx.data_ptr(), self.depth_coding.data_ptr(),
+                None, 0, None, None, None, None,
                 float(cfg.near_far_range[0]), float(cfg.depth_interval), 0, v, d, hf, wf, t, sa)
             run("backproject_fwd", "mvsd_backproject_fwd", self.feat_cl.data_ptr(), fdt, hf, wf,
                 geo.points.data_ptr(), geo.projection.data_ptr(), self.est_depth.data_ptr(),
@@ -199,16 +200,17 @@ class ScenePipeline:
                 self.g_est_dens.data_ptr(), sv, sy, sx, s_t, v, h, w, t, sa)
             run("depth_topk_bwd", "mvsd_depth_topk_bwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2],
                 sc[4], self.est_idx.data_ptr(), None, None, None, self.g_est_dens.data_ptr(), None,
+                None, 0, None, None,
                 self.g_cost_out.data_ptr(), float(cfg.near_far_range[0]), float(cfg.depth_interval), 0,
                 v, d, hf, wf, t, sa)
         if overlap:
             run("plane_sweep_fwd", "mvsd_plane_sweep_fwd", self.feat_cl.data_ptr(), fdt,
                 geo.neighbor_ids.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(),
-                self.variance.data_ptr(), vdt, CHANNELS_LAST, v, c, d, hf, wf, k, 0, st)
+                self.variance.data_ptr(), vdt, CHANNELS_LAST, v, c, d, hf, wf, k, 0, v, st)
             cur.wait_stream(self._side)
         run("plane_sweep_bwd", "mvsd_plane_sweep_bwd", self.g_variance.data_ptr(), vdt, CHANNELS_LAST,
             self.feat_cl.data_ptr(), fdt, geo.neighbor_ids.data_ptr(), geo.hom.data_ptr(),
-            geo.depth_values.data_ptr(), self.g_feat_cl.data_ptr(), v, c, d, hf, wf, k, 0, st)
+            geo.depth_values.data_ptr(), self.g_feat_cl.data_ptr(), v, c, d, hf, wf, k, 0, v, st)
         if overlap:
             cur.wait_stream(aux)
         run("unpack", "mvsd_unpack_nhwc_to_nchw", self.g_feat_cl.data_ptr(), self.g_feature.data_ptr(),

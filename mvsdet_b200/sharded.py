@@ -192,7 +192,7 @@ class ShardedSceneForward:
         begin, end = partition_views(n_views, world, rank)
         if end <= begin:
             return None
-        geo = self.hot.geometry(img_meta, device, view_slice=slice(begin, end))
+        geo = self.hot.geometry(img_meta, device, view_slice=slice(begin, end), prologue="host")
         views, nbr_local = halo_views(geo.neighbor_ids_host, begin, end)
         return LocalGeometry(geo=geo, views=views, neighbor_ids_local=nbr_local.to(device),
                              begin=begin, end=end)
@@ -236,7 +236,7 @@ class ShardedSceneForward:
         if end > begin:
             lg = geometry
             if lg is None:
-                geo = hot.geometry(img_meta, dev, view_slice=slice(begin, end))
+                geo = hot.geometry(img_meta, dev, view_slice=slice(begin, end), prologue="host")
                 views, nbr_local = halo_views(geo.neighbor_ids_host, begin, end)
                 lg = LocalGeometry(geo, views, nbr_local.to(dev), begin, end)
             geo = lg.geo

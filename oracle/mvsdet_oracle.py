@@ -43,6 +43,7 @@ __all__ = [
     "depth_values_for", "depth_probability", "sample_depth_prob",
     "compute_avg_depth", "compute_projection", "feature_intrinsics",
     "get_points", "backproject_weigh", "aggregate_views", "hot_path",
+    "lift", "get_camera_params", "compute_depth_scale", "process_rgb_raw", "nvs_consumers",
 ]
 
 
@@ -366,6 +367,87 @@ def aggregate_views(volume, valid):
     volume_mean = torch.where((count[0] == 0).unsqueeze(0),
                               torch.zeros_like(volume_mean), volume_mean)
     return volume_mean, count
+
+
+# --------------------------------------------------------------------------
+# f3. NVS-branch consumers of the path -- mvsdet.py:1158-1218, :1272-1313, :319-333, :488-494, :579-583
+# --------------------------------------------------------------------------
+def lift(x, y, z, intrinsics):
+    """Pixel (x, y) at depth z -> homogeneous camera coordinates (mvsdet.py:1300-1313; the
+    reference's hard-coded ``.cuda()`` calls are dropped, nothing else)."""
+    fx = intrinsics[:, 0, 0]
+    fy = intrinsics[:, 1, 1]
+    cx = intrinsics[:, 0, 2]
+    cy = intrinsics[:, 1, 2]
+    sk = intrinsics[:, 0, 1]
+    x_lift = (x - cx.unsqueeze(-1) + cy.unsqueeze(-1) * sk.unsqueeze(-1) / fy.unsqueeze(-1)
+              - sk.unsqueeze(-1) * y / fy.unsqueeze(-1)) / fx.unsqueeze(-1) * z
+    y_lift = (y - cy.unsqueeze(-1)) / fy.unsqueeze(-1) * z
+    return torch.stack((x_lift, y_lift, z, torch.ones_like(z)), dim=-1)
+
+
+def get_camera_params(uv, pose, intrinsics):
+    """Unit ray directions of pixels uv [B,N,2] for camera-to-world ``pose`` [B,4,4]
+    (mvsdet.py:1272-1298) -> (ray_dirs [B,N,3], cam_loc [B,3])."""
+    cam_loc = pose[:, :3, 3]
+    batch_size, num_samples, _ = uv.shape
+    depth = torch.ones((batch_size, num_samples))
+    x_cam = uv[:, :, 0].view(batch_size, -1)
+    y_cam = uv[:, :, 1].view(batch_size, -1)
+    z_cam = depth.view(batch_size, -1)
+    pixel_points_cam = lift(x_cam, y_cam, z_cam, intrinsics=intrinsics).permute(0, 2, 1)
+    world_coords = torch.bmm(pose, pixel_points_cam).permute(0, 2, 1)[:, :, :3]
+    ray_dirs = F.normalize(world_coords - cam_loc[:, None, :], dim=2)
+    return ray_dirs, cam_loc
+
+
+def compute_depth_scale(height, width, img_meta, stride, num_src):
+    """z component of the unit ray through every feature-level pixel of a camera with identity
+    pose: (1, num_src, h*w, 1).  Both reference variants: shared intrinsics
+    (compute_depth_scale, mvsdet.py:1158-1187) and a list of per-view intrinsics
+    (compute_depth_scale_MultiIntrin, :1189-1218)."""
+    indices = [torch.arange(height), torch.arange(width)]
+    uv = torch.stack(torch.meshgrid(*indices, indexing="ij"), dim=0)
+    uv = torch.flip(uv, dims=[0]).float()
+    uv = uv.reshape(2, -1).transpose(1, 0).unsqueeze(0)                    # (1, h*w, 2) as (x, y)
+    ratio = img_meta["ori_shape"][0] / (img_meta["img_shape"][0] / stride)
+    intr = img_meta["lidar2img"]["intrinsic"]
+    if isinstance(intr, (list, tuple)):
+        num_src = len(intr)
+        uv = uv.repeat(num_src, 1, 1)
+        intrinsic = torch.tensor(np.array(intr))
+        intrinsic[:, :2] /= ratio
+        pose = torch.eye(4).unsqueeze(0).repeat(num_src, 1, 1)
+        ray_dirs, _ = get_camera_params(uv, pose, intrinsic)
+        return ray_dirs[:, :, 2:].unsqueeze(0)
+    intrinsic = torch.tensor(np.array(intr))
+    intrinsic[:2] /= ratio
+    ray_dirs, _ = get_camera_params(uv, torch.eye(4)[None], intrinsic.unsqueeze(0))
+    return ray_dirs[0, :, 2:].unsqueeze(0).unsqueeze(0).repeat(1, num_src, 1, 1)
+
+
+def process_rgb_raw(orig_rgb, ratio, height, width, src_id):
+    """(n_src,3,H,W) images -> (1, n_nei, height*width, 3): bilinear 1/ratio down-sampling, crop,
+    re-layout (mvsdet.py:319-333)."""
+    assert ratio == 4
+    new_rgb = F.interpolate(orig_rgb[src_id], scale_factor=1. / ratio, mode="bilinear")
+    new_rgb = new_rgb[:, :, :height, :width]
+    return new_rgb.reshape(*new_rgb.shape[:2], -1).transpose(2, 1).unsqueeze(0)
+
+
+def nvs_consumers(prob_volume, est_depth_r, depth_coding, img_meta, stride, height, width):
+    """What the NVS branch derives from the path's outputs (mvsdet.py:488-494, :579, :583):
+    est_depth_r [V,h*w,1,T], depth_coding [V,1,h,w] ->
+    dict(depth_scale [V,h*w,1], est_ray_depth [V,h*w,1,T], ray_depth_coding [V,h*w,1],
+    opacity [V,Hf,Wf])."""
+    v = prob_volume.shape[0]
+    scale = compute_depth_scale(height, width, img_meta, stride, v).squeeze(0)            # (V,h*w,1)
+    est_ray_depth = est_depth_r / (scale.unsqueeze(-1).repeat(1, 1, 1, est_depth_r.shape[-1]) + 1e-8)
+    coding = depth_coding.reshape(v, 1, -1).transpose(2, 1)                               # (V,h*w,1)
+    ray_depth_coding = coding / (scale + 1e-8)
+    opacity = torch.max(prob_volume, dim=1)[0]
+    return dict(depth_scale=scale, est_ray_depth=est_ray_depth, ray_depth_coding=ray_depth_coding,
+                opacity=opacity)
 
 
 # --------------------------------------------------------------------------

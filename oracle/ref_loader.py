@@ -21,6 +21,12 @@ Reference entry points loaded (all under projects/NeRF-Det/nerfdet/):
   mvsdet.py:1124-1156            MVSDet._compute_projection
   mvsdet.py:1316-1327            get_points
   mvsdet.py:1372-1492            backproject_Weigh
+  mvsdet.py:1158-1218            MVSDet.compute_depth_scale, compute_depth_scale_MultiIntrin
+  mvsdet.py:1272-1313            get_camera_params, lift
+  mvsdet.py:319-333              MVSDet.process_rgb_raw
+The last two groups call ``.cuda()`` on freshly created tensors (mvsdet.py:1283, :1302, :1313);
+``cpu_cuda_shim()`` makes ``Tensor.cuda`` the identity while they run in this GPU-less container
+-- the executed source is still the reference's, unmodified.
 """
 from __future__ import annotations
 
@@ -34,9 +40,11 @@ import warnings
 REFERENCE_ROOT = os.environ.get("MVSDET_REFERENCE_ROOT", "/root/reference")
 _NERFDET = os.path.join(REFERENCE_ROOT, "projects", "NeRF-Det", "nerfdet")
 
-_FREE_FUNCS = ("knn", "get_nearest_pose_ids", "get_points", "backproject_Weigh")
+_FREE_FUNCS = ("knn", "get_nearest_pose_ids", "get_points", "backproject_Weigh",
+               "get_camera_params", "lift")
 _METHODS = ("collect_proj", "sample_depth_prob", "compute_avg_depth",
-            "_compute_projection")
+            "_compute_projection", "compute_depth_scale", "compute_depth_scale_MultiIntrin",
+            "process_rgb_raw")
 
 
 def available() -> bool:
@@ -86,6 +94,21 @@ def load() -> types.SimpleNamespace:
         setattr(out, name, ns[name])
     out.homo_warping = _load_module_py().homo_warping
     return out
+
+
+class cpu_cuda_shim:
+    """Context manager: ``Tensor.cuda()`` returns the tensor itself (build container has no GPU)."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self_, *a, **k: self_
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self._orig
+        return False
 
 
 def make_self(near_far_range, num_depth):

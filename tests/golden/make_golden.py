@@ -133,9 +133,52 @@ def reference_chain(ref, scene, training=True):
         gap=gap, rmse=rmse)
 
 
+def reference_nvs(ref, scene, chain):
+    """The NVS-branch consumers of the path, by the reference's own code:
+    compute_depth_scale[_MultiIntrin] (mvsdet.py:1158-1218 -> get_camera_params / lift), the
+    ray-depth conversions of extract_feat (:488-494, :583), opacity (:579) and process_rgb_raw
+    (:319-333).  get_camera_params / lift call ``.cuda()``: run under ref_loader.cpu_cuda_shim."""
+    cfg = scene["cfg"]
+    meta = scene["img_meta"]
+    self = ref_loader.make_self(cfg.near_far_range, cfg.num_depth)
+    stride = cfg.stride
+    height, width = meta["img_shape"][0] // stride, meta["img_shape"][1] // stride
+    v = cfg.n_views
+    with ref_loader.cpu_cuda_shim():
+        if isinstance(meta["lidar2img"]["intrinsic"], list):                       # :490-492
+            scale = ref.compute_depth_scale_MultiIntrin(self, height, width, "cpu", meta, stride, v)
+        else:                                                                      # :487-489
+            scale = ref.compute_depth_scale(self, height, width, "cpu", meta, stride, v)
+    cur_depth_scale = scale.squeeze(0)                                             # (V, h*w, 1)
+    est_depth = chain["est_depth"][:, :, :height, :width]
+    est_depth = est_depth.view(*est_depth.shape[:2], -1).transpose(2, 1).unsqueeze(2)   # :484
+    est_ray_depth = est_depth / (cur_depth_scale.unsqueeze(-1).repeat(1, 1, 1, est_depth.shape[-1]) + 1e-8)
+    depth_coding = chain["depth_coding"]                                           # (V,1,h,w)
+    dc = depth_coding.view(*depth_coding.shape[:2], -1).unsqueeze(0).transpose(3, 2)     # :562
+    ray_depth_coding = dc / (cur_depth_scale.unsqueeze(0) + 1e-8)                  # :583
+    opacity = torch.max(chain["prob_volume"], dim=1)[0]                            # :579
+    rgb = torch.rand(v, 3, cfg.pad_shape[0], cfg.pad_shape[1],
+                     generator=torch.Generator().manual_seed(77))
+    src_id = list(range(0, v, 2))
+    rgb_raw = ref.process_rgb_raw(self, rgb, stride, height, width, src_id)
+    return dict(depth_scale=scale, est_ray_depth=est_ray_depth, ray_depth_coding=ray_depth_coding,
+                opacity=opacity, rgb=rgb, src_id=np.asarray(src_id, dtype=np.int64), rgb_raw=rgb_raw)
+
+
 def main():
     ref = ref_loader.load()
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    only_nvs = "--only-nvs" in sys.argv
+    for name in ("scannet_tiny", "arkit_tiny"):
+        cfg, seed = CASES[name]
+        scene = make_scene(cfg, seed)
+        chain = reference_chain(ref, scene)
+        nvs = reference_nvs(ref, scene, chain)
+        path = os.path.join(out_dir, "nvs_" + name + ".npz")
+        np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in nvs.items()})
+        print(f"nvs_{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+    if only_nvs:
+        return
     for name, (cfg, seed) in CASES.items():
         scene = make_scene(cfg, seed)
         res = reference_chain(ref, scene)

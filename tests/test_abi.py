@@ -63,7 +63,7 @@ def test_prototype_arity_matches_ctypes_table():
 def test_load_info_and_status_strings():
     _lib = _build_if_needed()
     lib = _lib.load()
-    assert lib.mvsd_abi_version() == 1
+    assert lib.mvsd_abi_version() == _lib.ABI_VERSION == 2
     assert b"sm_100a" in lib.mvsd_build_info()
     assert lib.mvsd_status_string(0) == b"ok"
     assert lib.mvsd_status_string(1) == b"invalid argument"
@@ -77,15 +77,22 @@ def test_invalid_arguments_fail_before_any_launch():
     _lib = _build_if_needed()
     lib = _lib.load()
     before = lib.mvsd_launch_count()
-    st = lib.mvsd_plane_sweep_fwd(None, 0, None, None, None, None, 0, 0, 2, 8, 4, 4, 4, 0, 0, None)
+    st = lib.mvsd_plane_sweep_fwd(None, 0, None, None, None, None, 0, 0, 2, 8, 4, 4, 4, 0, 0, 2, None)
     assert st == _lib.ERR_INVALID_ARG and b"null" in lib.mvsd_last_error()
-    st = lib.mvsd_plane_sweep_fwd(None, 0, None, None, None, None, 0, 0, 0, 8, 4, 4, 4, 0, 0, None)
+    st = lib.mvsd_plane_sweep_fwd(None, 0, None, None, None, None, 0, 0, 0, 8, 4, 4, 4, 0, 0, 2, None)
     assert st == _lib.ERR_INVALID_ARG
-    st = lib.mvsd_plane_sweep_fwd(None, 0, None, None, None, None, 0, 0, 2, 6, 4, 4, 4, 0, 0, None)
+    st = lib.mvsd_plane_sweep_fwd(None, 0, None, None, None, None, 0, 0, 2, 6, 4, 4, 4, 0, 0, 2, None)
     assert st == _lib.ERR_UNSUPPORTED                    # C not a multiple of 4
+    one = ctypes.c_void_p(16)                            # non-null dummy: rejected before any dereference
+    st = lib.mvsd_plane_sweep_fwd(one, 0, one, one, one, one, 0, 0, 2, 8, 4, 4, 4, 2, 1, 2, None)
+    assert st == _lib.ERR_INVALID_ARG and b"exceed" in lib.mvsd_last_error()   # ref views [1,3) of 2
     st = lib.mvsd_depth_topk_fwd(None, 0, 0, 0, 0, None, None, None, None, None, None,
-                                 0.2, 0.4, 0, 1, 100, 4, 4, 3, None)
+                                 None, 0, None, None, None, None, 0.2, 0.4, 0, 1, 100, 4, 4, 3, None)
     assert st == _lib.ERR_UNSUPPORTED                    # D > 64
+    st = lib.mvsd_scene_setup(one, one, 0, one, one, one, one, one, 4, 4, 0, 4, None)
+    assert st == _lib.ERR_UNSUPPORTED                    # k must be <= V-1
+    st = lib.mvsd_scene_setup(one, one, 0, one, one, one, one, one, 4, 2, 3, 2, None)
+    assert st == _lib.ERR_INVALID_ARG                    # reference views [3,5) of 4
     st = lib.mvsd_backproject_fwd(None, 0, 4, 4, None, None, None, None, 0, 0, 0, 0, 0.2, 7, None,
                                   0, None, None, None, 1, 8, 4, 4, 3, 10, None)
     assert st == _lib.ERR_INVALID_ARG                    # bad mode

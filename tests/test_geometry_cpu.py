@@ -76,3 +76,51 @@ def test_view_slice_keeps_full_scene_neighbours():
     assert torch.equal(part.hom, full.hom[4:8])
     assert torch.equal(part.projection, full.projection[4:8])
     assert part.depth_values.shape == (4, cfg.num_depth)
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"V{c.n_views}{'pv' if c.per_view_intrinsics else ''}")
+def test_host_camera_block_reproduces_aten_bits(cfg):
+    """The host half of the device prologue (geometry.host_camera_block): numpy fp32 arithmetic
+    that must be ATen's, bit for bit -- K_feat (rows 0-1 / ratio), ref_proj = K_feat @ w2c (the
+    un-fused chain of ATen's batched small-matrix product) and its inverse -- on 30 seeded
+    scenes per configuration (120 scenes)."""
+    for seed in range(30):
+        meta = _meta(cfg, seed)
+        w2c_np, k_feat, ref_proj, inv_ref = G.host_camera_block(meta, cfg.stride)
+        intr, w2c = _meta_tensors(meta)
+        ratio = meta["ori_shape"][0] / (meta["img_shape"][0] / cfg.stride)
+        kf = O.feature_intrinsics(intr, ratio)
+        assert np.array_equal(k_feat, kf.numpy())
+        nbr = torch.zeros(cfg.n_views, 1, dtype=torch.long)
+        want, _ = O.collect_proj(w2c, kf, nbr)
+        assert np.array_equal(ref_proj, want.numpy()), f"ref_proj differs from ATen's matmul (seed {seed})"
+        assert np.array_equal(inv_ref, torch.inverse(want).numpy())
+        assert np.array_equal(w2c_np, w2c.numpy())
+
+
+def test_setup_kernel_arithmetic_restated_on_host():
+    """What csrc/scene_setup.cu computes, restated with numpy fp32/fp64 ops: the un-fused
+    4-term chain for nei_proj @ inverse(ref_proj) equals ATen's batched matmul bit for bit, and
+    the fp64 closed-form camera centres order the neighbours exactly as the reference's fp32
+    knn does on these scenes (the kernel itself is checked on the GPU, tests/test_gpu_geometry.py)."""
+    for cfg in CONFIGS[:2]:
+        for seed in range(10):
+            meta = _meta(cfg, seed)
+            w2c_np, k_feat, ref_proj, inv_ref = G.host_camera_block(meta, cfg.stride)
+            intr, w2c = _meta_tensors(meta)
+            k = min(2, cfg.n_views - 1)
+            nbr = O.get_nearest_pose_ids(torch.inverse(w2c), k)
+            # neighbour ids from fp64 centres
+            loc = np.linalg.inv(w2c_np.astype(np.float64))[:, :3, 3].astype(np.float32).astype(np.float64)
+            d2 = ((loc[:, None] - loc[None]) ** 2).sum(-1)
+            np.fill_diagonal(d2, np.inf)
+            mine = np.argsort(d2, axis=1, kind="stable")[:, :k]
+            assert np.array_equal(mine, nbr.numpy())
+            # homography chain
+            a = ref_proj[nbr.numpy()]                      # [V,k,4,4]
+            b = inv_ref[:, None]                           # [V,1,4,4]
+            acc = a[..., :, 0:1] * b[..., 0:1, :]
+            for kk in (1, 2, 3):
+                acc = acc + a[..., :, kk:kk + 1] * b[..., kk:kk + 1, :]
+            want = torch.matmul(torch.from_numpy(ref_proj)[nbr], torch.from_numpy(inv_ref).unsqueeze(1))
+            assert np.array_equal(acc, want.numpy())

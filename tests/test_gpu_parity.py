@@ -8,8 +8,6 @@ relative in fp32 (1e-2 with bf16 features).  Float comparisons use
 entries that cancel to ~0 (variance of three equal samples) are judged against
 the tensor's scale, as SURVEY.md "hard part 4" asks.
 """
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -20,9 +18,6 @@ from oracle import mvsdet_oracle as O
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4
-# experiment builds (e.g. -DMVSD_EXP_TMEM_PENDING, tuning 5=17): MVSD_TEST_EXTRA_VARIANTS=17 adds them to the
-# backward-variant parity tests; unset (the default) nothing changes
-EXTRA_VARIANTS = [int(x) for x in os.environ.get("MVSD_TEST_EXTRA_VARIANTS", "").split(",") if x.strip()]
 
 
 def _close(a, b, what, rtol=RTOL, atol_scale=1e-4, abs_floor=0.0):
@@ -89,8 +84,10 @@ def test_chain_fp32_vs_reference_golden(case, channels_first):
 def test_chain_bf16_features(case):
     """bf16 features / fp32 accumulation (BASELINE.json configs[1]).  The oracle
     is fed the same bf16-rounded features, so what is tested is the kernel's
-    fp32 arithmetic on bf16 inputs; the 1e-2 bar of the north star covers the
-    bf16-rounded gradient that autograd hands back."""
+    fp32 arithmetic on bf16 inputs.  The drop-in accumulates both backward kernels into one
+    fp32 accumulator (ops.FeatureGradSink) and hands the FPN an fp32 gradient, so the fp32 bar
+    (1e-4) holds for the gradients too; the north star's 1e-2 is only needed where a gradient is
+    rounded to bf16 (the ops-level API with a bf16 leaf, test_ops_level_bf16_leaf_gradient)."""
     scene, _ = load_golden(case)
     scene = dict(scene)
     scene["feature"] = scene["feature"].to(torch.bfloat16).float()
@@ -101,8 +98,52 @@ def test_chain_bf16_features(case):
     for key in ("variance", "volume_mean", "est_depth", "est_densities"):
         _close(res[key], ref[key], f"{case}:{key}")
     for key in ("g_feature_from_variance", "g_feature_from_voxels"):
-        _close(res[key], ref[key], f"{case}:{key}", rtol=1e-2, atol_scale=1e-2)
+        _close(res[key], ref[key], f"{case}:{key}")
     _close(res["g_cost_out"], ref["g_cost_out"], f"{case}:g_cost_out")
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES[:2])
+def test_ops_level_bf16_leaf_gradient(case):
+    """ops-level API with a bf16 channels-last LEAF: autograd hands the gradient back in the leaf's
+    dtype, i.e. rounded to bf16 -- the 1e-2 bar of the north star."""
+    from mvsdet_b200 import ops
+    scene, _ = load_golden(case)
+    scene = dict(scene)
+    scene["feature"] = scene["feature"].to(torch.bfloat16).float()
+    ref = oracle_chain(scene)
+    cfg = scene["cfg"]
+    dev = torch.device("cuda")
+    mod = _module(cfg, torch.bfloat16)
+    geo = mod.geometry(scene["img_meta"], dev)
+    leaf = scene["feature"].to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    leaf.requires_grad_(True)
+    var = ops.plane_sweep_variance(leaf, geo.neighbor_ids, geo.hom, geo.depth_values)
+    g, = torch.autograd.grad(var, leaf, scene["g_variance"].to(dev))
+    assert g.dtype == torch.bfloat16
+    _close(g.float(), ref["g_feature_from_variance"], f"{case}: bf16 leaf gradient", rtol=1e-2, atol_scale=1e-2)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_gradient_sink_matches_functional_autograd(case):
+    """One backward through both heads with the shared fp32 accumulator == the sum of the two
+    separately computed gradients; and the torch.library route (no sink) agrees."""
+    scene, gold = load_golden(case)
+    cfg = scene["cfg"]
+    dev = torch.device("cuda")
+    outs = []
+    for disp in (False, True):
+        feature = scene["feature"].to(dev).requires_grad_(True)
+        cost_out = scene["cost_out"].to(dev).requires_grad_(True)
+        from mvsdet_b200.hotpath import MVSDetHotPath
+        mod = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
+                            stride=cfg.stride, dispatcher_ops=disp)
+        res = mod(feature, scene["img_meta"], cost_regularization=lambda var: cost_out)
+        torch.autograd.backward([res["variance"], res["volume_mean"]],
+                                [scene["g_variance"].to(dev), scene["g_volume_mean"].to(dev)])
+        outs.append(feature.grad.clone())
+    want = torch.from_numpy(gold["g_feature_from_variance"]) + torch.from_numpy(gold["g_feature_from_voxels"])
+    _close(outs[0], want, f"{case}: sink gradient")
+    _close(outs[1], want, f"{case}: dispatcher gradient")
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -245,14 +286,12 @@ def test_single_view_scene_variance_is_zero():
     assert float(var.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 11, 14, 16] + EXTRA_VARIANTS)
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("case", ["scannet_tiny", "two_views", "wide_c"])
 def test_plane_sweep_bwd_variants(case, variant):
-    """Every opt-in plane-sweep backward (mvsd_set_tuning key 5: 1 pixel kernel,
-    2 scalar run kernel, 3 first packed run kernel, 4 block-merging, 5/6 two-/four-row blocks with two
-    pending columns, 7 lean run kernel, 8 / 11 the row hand-off kernels before the default one
-    (shared-memory slots + mbarriers; decisions per pixel / at fill time), 14 pipelined lean kernel) must give the reference gradient, like the default (slim hand-off with
-    pipelined loads)."""
+    """Both built plane-sweep backward kernels (test hook mvsd_set_tuning key 5: 0 = the
+    run-merging kernel of the feature dtype, 1 = the generic pixel-per-warp kernel that serves
+    k = 3, 4) must give the reference gradient."""
     from mvsdet_b200 import _lib
     scene, gold = load_golden(case)
     old = _lib.set_tuning(5, variant)
@@ -265,25 +304,118 @@ def test_plane_sweep_bwd_variants(case, variant):
 
 
 @pytest.mark.parametrize("hw", [(13, 21), (9, 7), (17, 40)])
-@pytest.mark.parametrize("variant", [0, 5, 7, 8, 11, 14, 16] + EXTRA_VARIANTS)
-def test_ragged_feature_map_sizes(hw, variant):
+@pytest.mark.parametrize("feature_dtype", [torch.float32, torch.bfloat16], ids=["f32_lean", "bf16_handoff"])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_ragged_feature_map_sizes(hw, variant, feature_dtype):
     """Feature maps whose height is not a multiple of the CTA's 4 rows and whose width is
     not a multiple of the 8-pixel run (partial runs, idle warps, hand-off with a missing
-    row below), default backward (slim hand-off) and the other row / hand-off / lean variants: whole
-    chain vs the oracle."""
+    row below), for the lean kernel (fp32 features), the hand-off kernel (bf16 features) and the
+    generic pixel kernel: whole chain vs the oracle on the same (rounded) features."""
     from mvsdet_b200 import _lib
     from mvsdet_b200.scene import make_scene, tiny_config
     h, w = hw
     cfg = tiny_config(n_views=4, channels=40, num_depth=6, img_shape=(4 * h - 1, 4 * w),
                       pad_shape=(4 * h, 4 * w), ori_shape=(16 * h - 4, 16 * w))
     scene = make_scene(cfg, seed=21)
+    if feature_dtype == torch.bfloat16:
+        scene["feature"] = scene["feature"].to(torch.bfloat16).float()
     ref = oracle_chain(scene)
     old = _lib.set_tuning(5, variant)
     try:
-        res = cuda_chain(scene)
+        res = cuda_chain(scene, feature_dtype=feature_dtype)
     finally:
         _lib.set_tuning(5, old)
     assert np.array_equal(res["count"].cpu().numpy().reshape(ref["count"].shape), ref["count"].numpy())
     assert np.array_equal(res["est_idx"].cpu().numpy(), ref["est_idx"].numpy())
     for key in ("variance", "volume_mean", "g_feature_from_variance", "g_feature_from_voxels"):
         _close(res[key], ref[key], f"{hw} variant {variant}: {key}")
+
+
+def _warp_pair(rot, trans, depth_values, c=8, h=9, w=11, seed=0):
+    """oracle vs kernel for an arbitrary homography: ref_proj = I, src_proj = [[rot, trans], [0, 1]]
+    (inverse(I) and the products with 0 / 1 are exact, so both sides see the same rot / trans)."""
+    from mvsdet_b200 import functional as F_
+    b = rot.shape[0]
+    src_proj = torch.eye(4).repeat(b, 1, 1)
+    src_proj[:, :3, :3] = rot
+    src_proj[:, :3, 3] = trans
+    ref_proj = torch.eye(4).repeat(b, 1, 1)
+    src = torch.randn(b, c, h, w, generator=torch.Generator().manual_seed(seed)).requires_grad_(True)
+    want = O.homo_warping(src, src_proj, ref_proj, depth_values)
+    g = torch.randn(want.shape, generator=torch.Generator().manual_seed(seed + 1))
+    gw, = torch.autograd.grad(want, src, g)
+    src_c = src.detach().cuda().requires_grad_(True)
+    got = F_.homo_warping(src_c, src_proj.cuda(), ref_proj.cuda(), depth_values.cuda())
+    gg, = torch.autograd.grad(got, src_c, g.cuda())
+    return want.detach(), got.detach().cpu(), gw, gg.cpu()
+
+
+def test_warp_with_cameras_facing_away():
+    """SURVEY hard part 2 / module.py:136: the reference divides by q.z with no z > 0 guard and no
+    epsilon.  (a) q.z changes sign inside the image (points behind the source camera are still
+    sampled, mirrored); (b) q.z == 0 exactly on every pixel -> inf / NaN grid -> grid_sample adds
+    nothing; (c) q.z tiny -> huge coordinates, outside.  Kernel == oracle (values and gradient)."""
+    dv = torch.tensor([[0.5, 1.0, 2.0, 4.0]])
+    # (a) z = (0.08 x + 0.03 y - 0.6) d + 0.2 crosses zero within the 11 x 9 map for every plane
+    rot = torch.tensor([[[1.0, 0.02, 0.3], [-0.01, 1.0, -0.2], [0.08, 0.03, -0.6]]])
+    trans = torch.tensor([[0.1, -0.05, 0.2]])
+    want, got, gw, gg = _warp_pair(rot, trans, dv)
+    behind = float(((rot[0, 2, 0] * torch.arange(11.0)[None] + rot[0, 2, 1] * torch.arange(9.0)[:, None] + rot[0, 2, 2]) * 1.0
+                    + trans[0, 2] <= 0).float().mean())
+    assert 0.05 < behind < 0.95, "the case is supposed to mix q.z > 0 and q.z <= 0"
+    assert float(want.abs().max()) > 0
+    _close(got, want, "warp with q.z of both signs")
+    _close(gg, gw, "warp backward with q.z of both signs")
+    # (b) rot row 2 and trans z are zero: q.z == 0 everywhere (x/0 = +-inf, 0/0 = NaN)
+    rot_b = rot.clone(); rot_b[0, 2] = 0
+    trans_b = trans.clone(); trans_b[0, 2] = 0
+    want, got, gw, gg = _warp_pair(rot_b, trans_b, dv)
+    assert float(want.abs().max()) == 0.0 and float(got.abs().max()) == 0.0
+    assert float(gg.abs().max()) == 0.0 and not bool(torch.isnan(got).any())
+    # (c) q.z ~ 1e-30: finite but astronomically large pixel coordinates
+    trans_c = trans_b.clone(); trans_c[0, 2] = 1e-30
+    want, got, gw, gg = _warp_pair(rot_b, trans_c, dv)
+    _close(got, want, "warp with tiny q.z")
+    assert not bool(torch.isnan(got).any())
+
+
+def test_warp_per_pixel_depth_values():
+    """homo_warping's [B,D,H,W] depth_values branch (module.py:130-133; unused by MVSDet)."""
+    gen = torch.Generator().manual_seed(4)
+    b, d, h, w = 2, 3, 9, 11
+    rot = torch.eye(3).repeat(b, 1, 1) + 0.02 * torch.randn(b, 3, 3, generator=gen)
+    trans = 0.3 * torch.randn(b, 3, generator=gen)
+    dv = 1.0 + 2.0 * torch.rand(b, d, h, w, generator=gen)
+    want, got, gw, gg = _warp_pair(rot, trans, dv)
+    _close(got, want, "per-pixel depth warp")
+    _close(gg, gw, "per-pixel depth warp backward")
+
+
+def test_out_of_range_neighbour_ids_are_ignored_not_dereferenced():
+    """a stale / un-rebased neighbour id must not read or RED outside the feature tensor:
+    the kernels treat it as 'no sample' (forward: that neighbour adds nothing; backward: no
+    gradient leaves for it), and the Python layer rejects reference views beyond the tensor."""
+    from mvsdet_b200 import ops
+    scene, gold = load_golden("scannet_tiny")
+    cfg = scene["cfg"]
+    dev = torch.device("cuda")
+    mod = _module(cfg)
+    geo = mod.geometry(scene["img_meta"], dev)
+    feat = ops.pack_features(scene["feature"].to(dev), torch.float32).detach().requires_grad_(True)
+    bad = geo.neighbor_ids.clone()
+    bad[0, 1] = cfg.n_views + 3           # out of range
+    bad[2, 0] = -1
+    var = ops.plane_sweep_variance(feat, bad, geo.hom, geo.depth_values)
+    # guard pages: a view-sized pad after the accumulator would be hit by an unchecked id; here the
+    # check is behavioural -- equal to the sweep with those neighbours' samples removed
+    hom_off = geo.hom.clone()
+    hom_off[0, 1] = 0; hom_off[2, 0] = 0          # all-zero homography: q.z == 0 -> no sample
+    ok = geo.neighbor_ids.clone()
+    want = ops.plane_sweep_variance(feat, ok, hom_off, geo.depth_values)
+    assert torch.equal(var, want)
+    g = scene["g_variance"].to(dev)
+    ga, = torch.autograd.grad(var, feat, g)
+    gb, = torch.autograd.grad(want, feat, g)
+    _close(ga, gb, "backward with out-of-range ids", rtol=1e-5, atol_scale=1e-6)
+    with pytest.raises(ValueError):
+        ops.plane_sweep_variance(feat, geo.neighbor_ids, geo.hom, geo.depth_values, ref_begin=1)
