@@ -134,33 +134,38 @@ def cpu_reference_step(scene, n_sample_views: int):
     return feature.grad, cost_out.grad
 
 
+CPU_SAMPLE_VIEWS = 4          # reference views swept per CPU step: FIXED (round-1 picked 1, 2 or 4 by a
+                              # wall-clock budget, which moved the number by 1.9x between runs)
+
+
 def time_cpu_reference(cfg, steps: int, warmup: int, budget_s: float):
+    """The oracle on the host cores: always ``CPU_SAMPLE_VIEWS`` of the scene's reference views per
+    step (every stage of the path is linear in the number of reference views; the neighbours are
+    still drawn from all V), ``warmup`` untimed + ``steps`` timed steps, MEDIAN step time, scaled to
+    a scene.  Only the number of timed steps is bounded by ``budget_s`` (never below 3)."""
     from mvsdet_b200.scene import make_scene
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     scene = make_scene(cfg, seed=0)
     v = cfg.n_views
-    vs = 1
+    vs = min(CPU_SAMPLE_VIEWS, v)
     t0 = time.perf_counter()
-    cpu_reference_step(scene, vs)                      # calibration, also a warm-up
-    t_one = time.perf_counter() - t0
-    total_steps = max(1, steps + warmup)
-    for cand in (4, 2):
-        if cand <= v and t_one * cand * total_steps <= budget_s:
-            vs = cand
-            break
+    cpu_reference_step(scene, vs)                      # first warm-up step, also the calibration
+    t_first = time.perf_counter() - t0
     for _ in range(max(0, warmup - 1)):
         cpu_reference_step(scene, vs)
+    n_timed = max(3, min(max(1, steps), int(budget_s / max(t_first, 1e-3))))
     times = []
-    for _ in range(max(1, steps)):
+    for _ in range(n_timed):
         t0 = time.perf_counter()
         cpu_reference_step(scene, vs)
         times.append(time.perf_counter() - t0)
-    t_step = sum(times) / len(times)
+    t_step = statistics.median(times)
     scenes_per_s = 1.0 / (t_step * v / vs)
-    sample = (f"{vs} of {v} reference views per step (plane sweep + top-k + back-projection "
-              f"fwd+bwd of the oracle, fp32, torch {torch.__version__} CPU), scaled x{v / vs:g} "
-              f"to a scene; {len(times)} timed steps, mean {t_step:.2f} s/step")
+    sample = (f"{vs} of {v} reference views per step, fixed (plane sweep + top-k + back-projection "
+              f"fwd+bwd of the oracle, fp32, torch {torch.__version__} CPU, {threads} threads), scaled "
+              f"x{v / vs:g} to a scene; {len(times)} timed steps, median {t_step:.3f} s/step "
+              f"(min {min(times):.3f}, max {max(times):.3f})")
     return scenes_per_s, t_step, threads, sample, len(times)
 
 
@@ -168,7 +173,7 @@ def run_reference_arm(args, cfg, cfg_json):
     rank, local, world = _dist_env()
     if rank != 0:
         return
-    val, t_step, threads, sample, nsteps = time_cpu_reference(cfg, args.steps, args.warmup, 150.0)
+    val, t_step, threads, sample, nsteps = time_cpu_reference(cfg, args.steps, args.warmup, 200.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": nsteps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
@@ -185,12 +190,174 @@ def run_reference_arm(args, cfg, cfg_json):
 # ---------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------
+SURVEY_PATH_MB = 3034.0     # algorithmic bytes of the path per scene, fwd+bwd, fp32 sizes
+
+
+def _build_pipes(cfg, dev, feat_dtype, mod, rank, capture=True):
+    from mvsdet_b200.pipeline import ScenePipeline
+    from mvsdet_b200.scene import make_scene
+    pipes, graphs, first_scene = [], [], None
+    for b in range(NBUF):
+        scene = make_scene(cfg, seed=1000 * rank + b)
+        pipe = ScenePipeline(cfg, dev, feature_dtype=feat_dtype)
+        pipe.set_geometry(mod.geometry(scene["img_meta"], dev))
+        pipe.load_scene(scene)
+        pipes.append(pipe)
+        if b == 0:
+            first_scene = scene
+    torch.cuda.synchronize()
+    if capture:
+        graphs = [p.capture() for p in pipes]
+    return pipes, graphs, first_scene
+
+
+def _time_steps(step_fn, steps, warmup, barrier):
+    """W untimed + K timed steps on the current stream, CUDA events, barrier + synchronize on both
+    sides; returns (ms_total, wall0, wall1)."""
+    for i in range(warmup):
+        step_fn(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record()
+    for i in range(steps):
+        step_fn(i)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), wall0, time.time()
+
+
+def _kernel_table(pipes, ksteps):
+    timers = {}
+    for i in range(ksteps):
+        pipes[i % NBUF].step(timers)
+    torch.cuda.synchronize()
+    abytes = pipes[0].algorithmic_bytes()
+    kernels = {}
+    for name, evs in timers.items():
+        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        kernels[name] = {"ms": round(ms, 5), "algorithmic_mb": round(abytes[name] / 1e6, 2),
+                         "gbs": round(abytes[name] / (ms * 1e-3) / 1e9, 1)}
+    return kernels, abytes
+
+
+def time_eager_gpu(cfg, scene, dev, reps=3):
+    """SURVEY.md 8d 'eager-GPU comparison': the reference's PyTorch path (the oracle's ATen ops on
+    CUDA tensors, fp32, ~150 eager launches with host syncs) on the SAME GPU and scene, fwd+bwd."""
+    from oracle import mvsdet_oracle as O
+    feature0 = scene["feature"].to(dev)
+    cost0 = scene["cost_out"].to(dev)
+    g_var = scene["g_variance"].to(dev)
+    g_vol = scene["g_volume_mean"].to(dev)
+
+    def step():
+        feature = feature0.clone().requires_grad_(True)
+        cost_out = cost0.clone().requires_grad_(True)
+        res = O.hot_path(feature, scene["img_meta"], lambda var: cost_out,
+                         near_far_range=cfg.near_far_range, num_depth=cfg.num_depth, topk=cfg.topk,
+                         n_voxels=cfg.n_voxels, voxel_size=cfg.voxel_size, stride=cfg.stride, training=True)
+        torch.autograd.backward([res["variance"], res["volume_mean"]], [g_var, g_vol])
+
+    step()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out = {"value": 1e3 / ms, "unit": UNIT, "ms_per_scene": round(ms, 3), "steps": reps,
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 2),
+           "what": "reference PyTorch path (oracle ops) on CUDA tensors, fp32, eager ATen kernels, same GPU"}
+    del feature0, cost0, g_var, g_vol
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sharded_leg(args, dev, rank, world, dist):
+    """BASELINE.json configs[2]: ONE test-time scene (V = --sharded-views, forward only) with its
+    reference views sharded over the ranks and the voxel partials combined over NVLink, against
+    the same forward on one GPU.  Reported as the ``sharded`` key of the N > 1 bench line."""
+    from mvsdet_b200 import sharded
+    from mvsdet_b200.hotpath import MVSDetHotPath
+    from mvsdet_b200.scene import SceneConfig, make_scene
+    cfg = SceneConfig(n_views=args.sharded_views)
+    scene = make_scene(cfg, seed=7, with_grads=False)          # the same scene on every rank
+    hot = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
+                        feature_dtype=torch.bfloat16)
+    feat = scene["feature"].to(dev)
+    cost = scene["cost_out"].to(dev)
+    iters = 30
+
+    def timed(fn, n=iters):
+        for _ in range(3):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # one GPU, whole scene (every rank runs it on its own GPU; no communication)
+    geo_full = hot.geometry(scene["img_meta"], dev)
+    whole = hot(feat, scene["img_meta"], cost_regularization=lambda var: cost, geometry=geo_full)
+    ms_whole = timed(lambda: hot(feat, scene["img_meta"], cost_regularization=lambda var: cost,
+                                 geometry=geo_full))
+    out = {"workload": f"BASELINE.json configs[2]: V={cfg.n_views} test-time scene, forward, reference views "
+                       f"sharded over {world} GPUs, voxel sums + counts combined once per scene",
+           "views": cfg.n_views, "ms_whole_scene_1gpu": round(ms_whole, 4),
+           "bytes": int(whole["volume_mean"].numel() * 4 + whole["count"].numel() * 4)}
+    pipe = sharded.ShardedScenePipeline(hot, cfg, dev)
+    pipe.load(scene["feature"], scene["cost_out"], scene["img_meta"])
+    results = {}
+    for mode in ("p2p", "nccl"):
+        try:
+            res = pipe.forward(mode)
+            torch.cuda.synchronize()
+            ok_count = bool(torch.equal(res["count"], whole["count"]))
+            err = float((res["volume_mean"].reshape(-1) - whole["volume_mean"].reshape(-1)).abs().max())
+            chk = res["volume_mean"].double().sum().reshape(1)
+            gathered = [torch.zeros_like(chk) for _ in range(world)]
+            dist.all_gather(gathered, chk)
+            flags = torch.tensor([int(ok_count), int(err <= 1e-5 * max(1.0, float(whole["volume_mean"].abs().max())))],
+                                 device=dev)
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            ms_lat = timed(lambda: pipe.forward(mode))
+            ms_thr = timed(lambda: pipe.forward_stream(mode, 8), n=6) / 8
+            results[mode] = {"ms_per_scene_latency": round(ms_lat, 4), "ms_per_scene_pipelined": round(ms_thr, 4),
+                             "counts_bit_exact": bool(flags[0].item()), "volume_close": bool(flags[1].item()),
+                             "max_abs_err_vs_1gpu": err,
+                             "replicas_identical": all(float(g) == float(gathered[0]) for g in gathered)}
+        except Exception as exc:                          # noqa: BLE001 -- keep the other mode's number
+            results[mode] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    out["modes"] = results
+    best = min((m for m in results if "ms_per_scene_pipelined" in results[m]),
+               key=lambda m: results[m]["ms_per_scene_pipelined"], default=None)
+    if best is not None:
+        out.update(collective=best, ms=results[best]["ms_per_scene_pipelined"],
+                   ms_latency=results[best]["ms_per_scene_latency"],
+                   speedup_vs_1gpu=round(ms_whole / results[best]["ms_per_scene_pipelined"], 3),
+                   speedup_vs_1gpu_latency=round(ms_whole / results[best]["ms_per_scene_latency"], 3),
+                   what_ms_is="per-scene time of a stream of scenes, the combine of scene i overlapped with "
+                              "the sweep of scene i+1 (two CUDA streams, double-buffered peer partials); "
+                              "ms_latency = one scene alone")
+    pipe.close()
+    return out
+
+
 def run_own_arm(args, cfg, cfg_json):
     import torch.distributed as dist
     from mvsdet_b200 import _lib
     from mvsdet_b200.hotpath import MVSDetHotPath
-    from mvsdet_b200.pipeline import ScenePipeline
-    from mvsdet_b200.scene import make_scene
 
     rank, local, world = _dist_env()
     if not torch.cuda.is_available():
@@ -205,23 +372,12 @@ def run_own_arm(args, cfg, cfg_json):
     feat_dtype = torch.bfloat16 if args.feature_dtype == "bf16" else torch.float32
     mod = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
                         stride=cfg.stride)
-    pipes, graphs = [], []
-    for b in range(NBUF):
-        scene = make_scene(cfg, seed=1000 * rank + b)
-        pipe = ScenePipeline(cfg, dev, feature_dtype=feat_dtype)
-        pipe.set_geometry(mod.geometry(scene["img_meta"], dev))
-        pipe.load_scene(scene)
-        pipes.append(pipe)
-        if b == 0:
-            host_scene = scene
-    torch.cuda.synchronize()
+    use_graph = not args.no_graph
+    pipes, graphs, host_scene = _build_pipes(cfg, dev, feat_dtype, mod, rank, capture=use_graph)
     launches_before = _lib.launch_count()
     pipes[0].step()
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - launches_before
-    use_graph = not args.no_graph
-    if use_graph:
-        graphs = [p.capture() for p in pipes]
 
     def one_step(i):
         if use_graph:
@@ -234,27 +390,28 @@ def run_own_arm(args, cfg, cfg_json):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def rank_max(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     # ---- value: device-resident inputs --------------------------------
-    for i in range(args.warmup):
-        one_step(i)
     sampler = ClockSampler(local)
     sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.time()
-    e0.record()
-    for i in range(args.steps):
-        one_step(i)
-    e1.record()
-    barrier()
-    wall1 = time.time()
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total, wall0, wall1 = _time_steps(one_step, args.steps, args.warmup, barrier)
+    ms_total = rank_max(ms_total)
     ms_per_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
+    # the same measurement over a long run (sustained clocks / power), when the driver's K is short
+    sustained = None
+    if args.steps < args.sustained_steps:
+        ms_s, ws0, ws1 = _time_steps(one_step, args.sustained_steps, 3, barrier)
+        ms_s = rank_max(ms_s)
+        sustained = {"value": world * args.sustained_steps / (ms_s * 1e-3), "unit": UNIT,
+                     "steps": args.sustained_steps, "ms_per_step": ms_s / args.sustained_steps,
+                     "clocks": sampler.summary(ws0, ws1)}
 
     # ---- e2e: host buffers through the public pipeline call -------------
     p0 = pipes[0]
@@ -271,8 +428,7 @@ def run_own_arm(args, cfg, cfg_json):
     barrier()
     e2, e3 = runner.run(host_in, e2e_steps)             # H2D / compute / D2H overlapped across steps
     barrier()
-    wall2 = time.time()
-    ms_e2e = e2.elapsed_time(e3)
+    ms_e2e = rank_max(e2.elapsed_time(e3))
     # the same call without overlap (one stream), for reference
     for _ in range(2):
         p0.run_host(graphs[0] if use_graph else None)
@@ -284,39 +440,38 @@ def run_own_arm(args, cfg, cfg_json):
     e5.record()
     barrier()
     ms_e2e_serial = e4.elapsed_time(e5) / min(e2e_steps, 10)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
     e2e_value = world * e2e_steps / (ms_e2e * 1e-3)
     sampler.stop()
     clocks = sampler.summary(wall0, wall1)
     # sanity of the e2e result: compare the host copy of the outputs with the device ones
     e2e_ok = bool(torch.equal(host["count"], p0.count.cpu()))
+    h2d_parts = {n: getattr(p0, n).numel() * getattr(p0, n).element_size() for n in p0.INPUTS}
 
     # ---- per-kernel device times (CUDA events around each launch, same stream)
-    timers = {}
     ksteps = max(3, min(args.steps, 30))
-    for i in range(ksteps):
-        pipes[i % NBUF].step(timers)
-    torch.cuda.synchronize()
+    kernels, abytes = _kernel_table(pipes, ksteps)
     peak, peak_src = _peaks()
-    abytes = p0.algorithmic_bytes()
-    kernels = {}
-    for name, evs in timers.items():
-        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
-        kernels[name] = {"ms": round(ms, 5), "algorithmic_mb": round(abytes[name] / 1e6, 2),
-                         "gbs": round(abytes[name] / (ms * 1e-3) / 1e9, 1)}
+    path_names = [n for n in kernels if n not in ("pack", "unpack")]
     top = max(kernels, key=lambda n: kernels[n]["ms"])
     total_ms = sum(k["ms"] for k in kernels.values())
     achieved = kernels[top]["gbs"]
+    own_path_mb = sum(abytes[n] for n in path_names) / 1e6
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes[top],
                 "kernel_ms": kernels[top]["ms"],
                 "share_of_step": round(kernels[top]["ms"] / total_ms, 3),
-                "path_achieved_gbs": round(sum(abytes.values()) / (ms_per_step * 1e-3) / 1e9, 1),
-                "path_frac": round(sum(abytes.values()) / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
+                # whole path: SURVEY.md 8(d)'s 3 034 MB per scene (fp32 sizes, pack / unpack NOT counted)
+                "path_algorithmic_mb": SURVEY_PATH_MB,
+                "path_achieved_gbs": round(SURVEY_PATH_MB * 1e6 / (ms_per_step * 1e-3) / 1e9, 1),
+                "path_frac": round(SURVEY_PATH_MB * 1e6 / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                # the same with the bytes this configuration actually has to move (bf16 features are smaller)
+                "path_algorithmic_mb_own_dtypes": round(own_path_mb, 1),
+                "path_frac_own_dtypes": round(own_path_mb * 1e6 / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                "layout_overhead": {"what": "pack (FPN fp32 NCHW -> channels-last) + unpack of the gradient: "
+                                            "self-inflicted layout cost, not algorithmic bytes",
+                                    "mb": round((abytes["pack"] + abytes["unpack"]) / 1e6, 1),
+                                    "ms": round(kernels["pack"]["ms"] + kernels["unpack"]["ms"], 5)}}
     ncu_traffic = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(ncu_traffic):
         try:
@@ -327,9 +482,6 @@ def run_own_arm(args, cfg, cfg_json):
             if red:
                 # the scatter kernel's second stream: fp32 REDs into L2.  Ceiling measured by
                 # tools/microbench_red.cu on this pool's B200 (profiles/r01_b_microbench_red.txt).
-                # Up to round 1e this stream (3.6 GB at > 80 % of the ceiling) was the limiter; with
-                # the row hand-off it is 2.7 GB and the kernel is bound by instructions per pixel at
-                # 12 warps/SM (issue-active 49 %) -- reported for that reason.
                 red_gbs = red / (kernels[top]["ms"] * 1e-3) / 1e9
                 roofline["limiter"] = {"what": "fp32 red.global.add.v4 payload into L2 (ncu l1tex2xbar write bytes)",
                                        "red_payload_bytes": red, "achieved_gbs": round(red_gbs, 1),
@@ -338,7 +490,7 @@ def run_own_arm(args, cfg, cfg_json):
         except Exception:
             pass
 
-    # ---- the autograd drop-in (MVSDetHotPath + torch.autograd, host geometry every call):
+    # ---- the autograd drop-in (MVSDetHotPath + torch.autograd, scene geometry every call):
     # what a maintainer gets from INTEGRATION.md level 1, wall clock incl. host work
     module_api = None
     if world == 1:
@@ -358,21 +510,58 @@ def run_own_arm(args, cfg, cfg_json):
         for _ in range(5):
             module_step()
         torch.cuda.synchronize()
+        n_mod = 60
         t0 = time.perf_counter()
-        n_mod = 30
         for _ in range(n_mod):
             module_step()
+        t_host = (time.perf_counter() - t0) / n_mod * 1e3          # host time to ENQUEUE a scene
         torch.cuda.synchronize()
         ms_mod = (time.perf_counter() - t0) / n_mod * 1e3
         module_api = {"value": 1e3 / ms_mod, "unit": UNIT, "ms_per_scene": round(ms_mod, 4), "steps": n_mod,
-                      "what": "MVSDetHotPath forward + torch.autograd backward, scene geometry "
-                              "recomputed on the host every call, caching allocator, no CUDA graph"}
+                      "host_enqueue_ms_per_scene": round(t_host, 4),
+                      "fraction_of_graph_value": round((1e3 / ms_mod) / value, 4),
+                      "what": "MVSDetHotPath forward + torch.autograd backward, scene geometry rebuilt every "
+                              "call (two host ATen calls + one setup kernel), shared fp32 gradient accumulator, "
+                              "caching allocator, no CUDA graph"}
         del hot, m_feat, m_cost
+
+    # ---- fp32-feature line (1e-4 parity is proven on fp32 features; their backward is the lean kernel)
+    f32_line = None
+    if world == 1 and feat_dtype == torch.bfloat16 and not args.no_extras:
+        pipes32, graphs32, _ = _build_pipes(cfg, dev, torch.float32, mod, rank, capture=use_graph)
+
+        def step32(i):
+            if use_graph:
+                graphs32[i % NBUF].replay()
+            else:
+                pipes32[i % NBUF].step()
+        n32 = max(20, min(args.steps, 100))
+        ms32, _, _ = _time_steps(step32, n32, 3, barrier)
+        k32, _ = _kernel_table(pipes32, 10)
+        f32_line = {"value": n32 / (ms32 * 1e-3), "unit": UNIT, "steps": n32, "ms_per_step": ms32 / n32,
+                    "dtype": "f32 features, f32 accumulate",
+                    "kernels_ms": {n: k32[n]["ms"] for n in k32}}
+        del pipes32, graphs32
+        torch.cuda.empty_cache()
+
+    eager = None
+    if world == 1 and not args.no_extras:
+        try:
+            eager = time_eager_gpu(cfg, host_scene, dev)
+        except Exception as exc:                       # noqa: BLE001
+            eager = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+
+    sharded_line = None
+    if world > 1 and not args.no_sharded:
+        try:
+            sharded_line = run_sharded_leg(args, dev, rank, world, dist)
+        except Exception as exc:                       # noqa: BLE001
+            sharded_line = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank == 0:
         cpu_line = None
         if world == 1 and not args.no_cpu_baseline:
-            val, t_step, threads, sample, _ = time_cpu_reference(cfg, 2, 1, 25.0)
+            val, t_step, threads, sample, _ = time_cpu_reference(cfg, 3, 1, 30.0)
             cpu_line = {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -385,14 +574,27 @@ def run_own_arm(args, cfg, cfg_json):
                     "d2h_bytes_per_step": p0.d2h_bytes(), "steps": e2e_steps,
                     "ms_per_step": ms_e2e / e2e_steps, "outputs_match_device": e2e_ok,
                     "overlap": "H2D / compute / D2H on three streams over %d buffer sets" % NBUF,
-                    "ms_per_step_serial": ms_e2e_serial},
+                    "ms_per_step_serial": ms_e2e_serial,
+                    "h2d_bytes_by_input": h2d_parts,
+                    "h2d_fraction_g_variance": round(h2d_parts["g_variance"] / p0.h2d_bytes(), 3),
+                    "note": "g_variance (the gradient the cost-regularisation net returns) is 90 % of the "
+                            "upload: on a real detector it is produced on the device; here it is a synthetic "
+                            "input and is copied in every step, so e2e is PCIe-bound"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "cuda_graph": use_graph,
             "roofline": roofline, "kernels": kernels,
         }
+        if sustained is not None:
+            line["sustained"] = sustained
         if module_api is not None:
             line["module_api"] = module_api
+        if f32_line is not None:
+            line["f32_features"] = f32_line
+        if eager is not None:
+            line["eager_gpu"] = eager
+        if sharded_line is not None:
+            line["sharded"] = sharded_line
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
         print(json.dumps(line), flush=True)
@@ -412,6 +614,11 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--sustained-steps", type=int, default=600,
+                    help="a second timed run of this many steps when --steps is shorter (sustained clocks)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32-feature and eager-GPU legs")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the view-sharded V=80 leg")
+    ap.add_argument("--sharded-views", type=int, default=80)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "own" else 1)
 

@@ -266,6 +266,19 @@ int mvsd_voxel_reduce_p2p(const void* const* part_ptrs, void* const* out_ptrs,
                           int32_t* count_local, int world, int rank, int layout, int C, int N,
                           void* stream);
 
+/* Backward of a view-sharded scene: the owner of each reference view adds the gradient
+ * contributions its peers accumulated for that view as a HALO (neighbour) view
+ * (mvsd_plane_sweep_bwd scatters into block + halo maps).  g_ptrs: DEVICE array of `world`
+ * peer pointers to the ranks' fp32 gradient buffers [V_local][view_elems] (block views
+ * first).  CSR pull table of this rank: owned view d receives sources
+ * pull_sources[2*q] = peer rank, pull_sources[2*q+1] = view index in that peer's buffer, for
+ * q in [pull_offsets[d], pull_offsets[d+1]).  Deterministic (table order).  The caller puts
+ * a cross-rank barrier before (all backward kernels done) and after (before the buffers are
+ * zeroed again) this call.                                                              */
+int mvsd_halo_reduce_p2p(void* const* g_ptrs, const int32_t* pull_offsets,
+                         const int32_t* pull_sources, int world, int rank, int n_own,
+                         int64_t view_elems, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mvsd_prob_norm_bwd": ([_p, _p, _p, _l, _l, _l, _l, _i, _i, _i, _i, _p], _i),
     "mvsd_voxel_normalize": ([_p, _p, _p, _i, _i, _i, _p], _i),
     "mvsd_voxel_reduce_p2p": ([_p, _p, _p, _i, _i, _i, _i, _i, _p], _i),
+    "mvsd_halo_reduce_p2p": ([_p, _p, _p, _i, _i, _i, _l, _p], _i),
 }
 
 _lock = threading.Lock()

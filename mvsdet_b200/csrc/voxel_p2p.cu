@@ -90,10 +90,62 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PParams p) {
   }
 }
 
+// Backward of a view-sharded scene: a rank's plane-sweep backward scatters into the gradient maps
+// of its block views AND of its halo views (neighbours owned by other ranks).  The owner of a view
+// adds the halo contributions of its peers to its own map: one pull kernel over NVLink peer
+// pointers, one CTA column per (owned view, 16-byte chunk), sources in table order -> the same
+// summation order on every run (deterministic).  pulls: CSR over the owned views --
+// offs[d] .. offs[d+1] index (src_rank, src_local_view) pairs.
+struct HaloParams {
+  float* const* g;            // device array [world]: peers' gradient buffers [V_local][view_elems] fp32
+  const int32_t* offs;        // [n_own + 1]
+  const int32_t* src;         // [n_pull][2]
+  int rank, n_own;
+  size_t view_elems;          // H*W*C, multiple of 4
+};
+
+__global__ void __launch_bounds__(256) halo_reduce_kernel(const HaloParams p) {
+  const int d = blockIdx.y;
+  const int b = p.offs[d], e = p.offs[d + 1];
+  if (b == e) return;
+  float* mine = p.g[p.rank] + (size_t)d * p.view_elems;
+  const size_t n4 = p.view_elems >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 s = *reinterpret_cast<const float4*>(mine + (i << 2));
+    for (int q = b; q < e; ++q) {
+      const float* peer = p.g[p.src[2 * q]] + (size_t)p.src[2 * q + 1] * p.view_elems;
+      const float4 t = ld_peer4(peer + (i << 2));
+      s.x = __fadd_rn(s.x, t.x); s.y = __fadd_rn(s.y, t.y);
+      s.z = __fadd_rn(s.z, t.z); s.w = __fadd_rn(s.w, t.w);
+    }
+    *reinterpret_cast<float4*>(mine + (i << 2)) = s;
+  }
+}
+
 }  // namespace
 }  // namespace mvsd
 
 using namespace mvsd;
+
+extern "C" int mvsd_halo_reduce_p2p(void* const* g_ptrs, const int32_t* pull_offsets,
+                                    const int32_t* pull_sources, int world, int rank, int n_own,
+                                    int64_t view_elems, void* stream) {
+  if (!g_ptrs || !pull_offsets || !pull_sources)
+    return fail(MVSD_ERR_INVALID_ARG, "halo_reduce_p2p: null pointer");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(MVSD_ERR_INVALID_ARG, "halo_reduce_p2p: bad world/rank (%d/%d)", rank, world);
+  if (n_own <= 0 || n_own > 65535 || view_elems <= 0 || (view_elems & 3))
+    return fail(MVSD_ERR_INVALID_ARG, "halo_reduce_p2p: bad view count / size");
+  HaloParams p;
+  p.g = reinterpret_cast<float* const*>(g_ptrs);
+  p.offs = pull_offsets; p.src = pull_sources; p.rank = rank; p.n_own = n_own;
+  p.view_elems = (size_t)view_elems;
+  const size_t want = ((size_t)view_elems / 4 + 255) / 256;
+  dim3 grid((unsigned)(want < 64 ? want : 64), (unsigned)n_own);
+  halo_reduce_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  count_launch();
+  return check_launch("halo_reduce_p2p");
+}
 
 extern "C" int mvsd_voxel_reduce_p2p(const void* const* part_ptrs, void* const* out_ptrs,
                                      int32_t* count_local, int world, int rank, int layout, int C,

@@ -37,8 +37,8 @@ import torch.distributed as dist
 
 from ._lib import CHANNELS_FIRST, CHANNELS_LAST
 
-__all__ = ["partition_views", "halo_views", "pack_partials", "unpack_partials",
-           "allreduce_partials", "LocalGeometry", "ShardedSceneForward"]
+__all__ = ["partition_views", "halo_views", "halo_pull_table", "pack_partials", "unpack_partials",
+           "allreduce_partials", "LocalGeometry", "ShardedSceneForward", "ShardedScenePipeline"]
 
 
 def halo_views(neighbor_ids: torch.Tensor, begin: int, end: int) -> Tuple[List[int], torch.Tensor]:
@@ -54,6 +54,36 @@ def halo_views(neighbor_ids: torch.Tensor, begin: int, end: int) -> Tuple[List[i
     local = torch.tensor([[lut[int(x)] for x in row] for row in nbr.tolist()],
                          dtype=torch.int32).reshape(nbr.shape[0], nbr.shape[1] if nbr.dim() > 1 else 0)
     return order, local
+
+
+def halo_pull_table(neighbor_ids: torch.Tensor, world: int, rank: int):
+    """Backward of a view-sharded scene: which peers hold gradient contributions for the views this
+    rank owns.  ``neighbor_ids`` [V,k] are the FULL scene's ids (every rank computes the same
+    table from them).  Rank q's sweep backward scatters into its halo views -- the neighbours of
+    its block that it does not own; the owner pulls them.  Returns (offsets int32 [n_own+1],
+    sources int32 [n_pull,2] = (peer rank, view index in the peer's local buffer)), CSR over this
+    rank's owned views, peers in rank order.  Pure host logic (tested on CPU)."""
+    nbr = neighbor_ids.to(torch.int64).cpu()
+    v = nbr.shape[0]
+    begin, end = partition_views(v, world, rank)
+    per_view: List[List[Tuple[int, int]]] = [[] for _ in range(end - begin)]
+    for q in range(world):
+        if q == rank:
+            continue
+        qb, qe = partition_views(v, world, q)
+        if qe <= qb:
+            continue
+        order, _ = halo_views(nbr[qb:qe], qb, qe)
+        for local_idx, g in enumerate(order):
+            if local_idx >= qe - qb and begin <= g < end:           # a halo view of q that this rank owns
+                per_view[g - begin].append((q, local_idx))
+    offs = [0]
+    src: List[Tuple[int, int]] = []
+    for lst in per_view:
+        src.extend(lst)
+        offs.append(len(src))
+    return (torch.tensor(offs, dtype=torch.int32),
+            torch.tensor(src, dtype=torch.int32).reshape(-1, 2))
 
 
 @dataclass
@@ -119,6 +149,10 @@ class P2PVoxelReducer:
 
         red = P2PVoxelReducer(C, N, channels_first, device, group)
         volume_mean, count = red(volume_sum, count)        # identical bits on every rank
+
+    LIFETIME: the returned tensors are views of the reducer's peer-mapped result buffer, which the
+    next call (this rank's and the peers' P2P stores) overwrites.  Clone them to keep them
+    (``ShardedSceneForward`` does).
     """
 
     def __init__(self, channels: int, n_voxels: int, channels_first: bool, device, group=None):
@@ -276,7 +310,11 @@ class ShardedSceneForward:
             feature, img_meta, cost_net, geometry,
             partial_out=self._reducer.partial_buffers() if use_p2p else None)
         if use_p2p:
+            # the reducer's result buffers are peer-mapped and reused by the next scene (peers store
+            # into them): hand the caller its own copy, as the NCCL branch does (the reference
+            # keeps every scene's volume in a list and stacks them later, mvsdet.py:681-696)
             volume_mean, count = self._reducer(vol_sum.detach(), count)
+            volume_mean, count = volume_mean.clone(), count.clone()
         else:
             buf = pack_partials(vol_sum.detach(), count)
             allreduce_partials(buf, self.group)
@@ -286,3 +324,253 @@ class ShardedSceneForward:
               else volume_mean.unflatten(1, (nx, ny, nz)))
         return dict(volume_mean=vm, valid=count.view(1, nx, ny, nz).float(), count=count,
                     view_range=(begin, end))
+
+
+class ShardedScenePipeline:
+    """Pre-allocated view-sharded forward (+ backward) of ONE large scene per rank -- the
+    multi-GPU counterpart of ``pipeline.ScenePipeline`` (BASELINE.json configs[2] / [3]).
+
+    Per rank: the fp32 FPN maps of its block of reference views plus the halo views (the pose
+    neighbours it does not own) are resident ("pre-placed halos", SURVEY.md 8e caveat 1); the
+    chain  pack -> plane sweep -> top-k -> back-projection(SUM)  writes the partial voxel sums and
+    counts straight into a peer-mapped buffer and is replayed as ONE CUDA graph; the combine
+    (sum over ranks + ``sum / (count + 1e-8)``, mvsdet.py:511-515, :681-682) is either
+    ``mvsd_voxel_reduce_p2p`` over NVLink peer pointers between two symmetric-memory barriers
+    ("p2p") or NCCL all-reduces + ``mvsd_voxel_normalize`` ("nccl").  Partial and result buffers are
+    double-buffered, so in a stream of scenes the combine of scene i runs on a second CUDA
+    stream under the sweep of scene i+1 (``forward_stream``).
+
+    Backward (``backward``): every rank holds ``g_volume_mean`` (replicated, like the forward's
+    result) and the gradient its cost-regularisation net returned for ITS views' variance;
+    back-projection / prob-norm / top-k / sweep backward run locally into one fp32 accumulator
+    over block + halo views, then each owner pulls its peers' halo contributions over NVLink
+    (``mvsd_halo_reduce_p2p``): the result is dL/dfeature for the rank's own block -- a
+    reduce-scatter of the scene's feature gradient with 2-4 views of traffic per rank."""
+
+    def __init__(self, hot_path, cfg, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("ShardedScenePipeline needs an initialised process group")
+        self.hot, self.cfg, self.device = hot_path, cfg, torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self._lib = _lib
+        self._symm = symm
+        self.c = cfg.channels
+        self.n = cfg.n_voxels[0] * cfg.n_voxels[1] * cfg.n_voxels[2]
+        self.total = self.c * self.n
+        dev = self.device
+        self.part = [symm.empty(self.total + self.n, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.out = [symm.empty(self.total + self.n, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.h_part = [symm.rendezvous(t, self.group) for t in self.part]
+        self.h_out = [symm.rendezvous(t, self.group) for t in self.out]
+        self.count_local = [torch.empty(self.n, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.nccl_out = [torch.empty(self.total, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.s_comm = torch.cuda.Stream(device=dev)
+        self._ev_part = [None, None]      # partials of slot written (compute stream)
+        self._ev_free = [None, None]      # slot's partial buffer consumed by the combine (comm stream)
+        self._graphs = [None, None]
+        self.lg: Optional[LocalGeometry] = None
+        self._g_feat = None
+        self._slot = 0
+
+    # ------------------------------------------------------------------ setup
+    def load(self, feature: torch.Tensor, cost_out: torch.Tensor, img_meta: dict) -> None:
+        """Place this rank's share of a scene: ``feature`` [V,C,Hf,Wf] fp32 and ``cost_out``
+        [V,2,D,Hf,Wf] (host or device, ALL views; only block + halo maps are kept)."""
+        hot, cfg, dev = self.hot, self.cfg, self.device
+        v_all = feature.shape[0]
+        begin, end = partition_views(v_all, self.world, self.rank)
+        if end <= begin:
+            raise ValueError("more ranks than reference views")
+        geo_full = hot.geometry(img_meta, "cpu", prologue="host")           # ids of the whole scene
+        self.nbr_full = geo_full.neighbor_ids_host
+        geo = hot.geometry(img_meta, dev, view_slice=slice(begin, end), prologue="host")
+        views, nbr_local = halo_views(geo.neighbor_ids_host, begin, end)
+        self.lg = LocalGeometry(geo, views, nbr_local.to(dev), begin, end)
+        vl, vb = len(views), end - begin
+        d, t = cfg.num_depth, cfg.topk
+        hf, wf = cfg.feat_hw
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.feature = feature[views].to(dev, dtype=torch.float32).contiguous()
+        self.cost_out = cost_out[begin:end].to(dev, dtype=torch.float32).contiguous()
+        self.feat_cl = torch.empty((vl, hf, wf, self.c), dtype=hot.feature_dtype, device=dev)
+        self.variance = torch.empty((vb, d, hf, wf, self.c), dtype=hot.variance_dtype, device=dev)
+        self.est_depth = torch.empty((vb, t, hf, wf), **f32)
+        self.est_dens = torch.empty((vb, t, hf, wf), **f32)
+        self.est_idx = torch.empty((vb, t, hf, wf), dtype=torch.int64, device=dev)
+        self.vl, self.vb = vl, vb
+        self._graphs = [None, None]
+        self._g_feat = None
+        torch.cuda.synchronize(dev)
+
+    def _code(self, dtype):
+        return self._lib.BF16 if dtype == torch.bfloat16 else self._lib.F32
+
+    def _enqueue_compute(self, slot: int) -> None:
+        """pack -> sweep -> top-k -> back-projection(SUM) into part[slot]; current stream; capturable."""
+        lib, cfg, lg, geo = self._lib, self.cfg, self.lg, self.lg.geo
+        st = torch.cuda.current_stream().cuda_stream
+        vl, vb, c = self.vl, self.vb, self.c
+        d, t, k = cfg.num_depth, cfg.topk, geo.k
+        hf, wf = cfg.feat_hw
+        fdt, vdt = self._code(self.hot.feature_dtype), self._code(self.hot.variance_dtype)
+        lib.call("mvsd_pack_nchw_to_nhwc", self.feature.data_ptr(), self.feat_cl.data_ptr(), fdt, vl, c, hf, wf, st)
+        lib.call("mvsd_plane_sweep_fwd", self.feat_cl.data_ptr(), fdt, lg.neighbor_ids_local.data_ptr(),
+                 geo.hom.data_ptr(), geo.depth_values.data_ptr(), self.variance.data_ptr(), vdt,
+                 CHANNELS_LAST, vb, c, d, hf, wf, k, 0, vl, st)
+        sc = self.cost_out.stride()
+        lib.call("mvsd_depth_topk_fwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2], sc[4], None, None,
+                 self.est_depth.data_ptr(), self.est_dens.data_ptr(), self.est_idx.data_ptr(), None,
+                 None, 0, None, None, None, None, float(cfg.near_far_range[0]), float(cfg.depth_interval), 0,
+                 vb, d, hf, wf, t, st)
+        sv, s_t, sy, sx = self.est_depth.stride()
+        part = self.part[slot]
+        lib.call("mvsd_backproject_fwd", self.feat_cl.data_ptr(), fdt, hf, wf, geo.points.data_ptr(),
+                 geo.projection.data_ptr(), self.est_depth.data_ptr(), self.est_dens.data_ptr(), sv, sy, sx, s_t,
+                 float(cfg.voxel_size[2]), self._lib.BP_SUM, part.data_ptr(), CHANNELS_FIRST,
+                 part[self.total:].data_ptr(), None, None, vb, c, geo.height, geo.width, t, self.n, st)
+
+    def _compute(self, slot: int, use_graph: bool = True) -> None:
+        if not use_graph:
+            self._enqueue_compute(slot)
+            return
+        if self._graphs[slot] is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._enqueue_compute(slot)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_compute(slot)
+            self._graphs[slot] = g
+        self._graphs[slot].replay()
+
+    def _combine(self, slot: int, mode: str) -> Dict[str, torch.Tensor]:
+        """sum over ranks + normalise, on the current stream -> views of this slot's result buffers"""
+        c, n, total = self.c, self.n, self.total
+        nx, ny, nz = self.cfg.n_voxels
+        st = torch.cuda.current_stream().cuda_stream
+        if mode == "p2p":
+            self.h_part[slot].barrier(channel=0)
+            self._lib.call("mvsd_voxel_reduce_p2p", self.h_part[slot].buffer_ptrs_dev,
+                           self.h_out[slot].buffer_ptrs_dev, self.count_local[slot].data_ptr(), self.world,
+                           self.rank, CHANNELS_FIRST, c, n, st)
+            self.h_out[slot].barrier(channel=0)
+            vol = self.out[slot][:total].view(c, nx, ny, nz)
+            count = self.out[slot][total:].view(torch.int32)
+        elif mode == "nccl":
+            part = self.part[slot]
+            dist.all_reduce(part[:total], op=dist.ReduceOp.SUM, group=self.group)
+            cnt = part[total:].view(torch.int32)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=self.group)
+            self.count_local[slot].copy_(cnt)
+            self._lib.call("mvsd_voxel_normalize", part.data_ptr(), cnt.data_ptr(),
+                           self.nccl_out[slot].data_ptr(), CHANNELS_FIRST, c, n, st)
+            vol = self.nccl_out[slot].view(c, nx, ny, nz)
+            count = self.count_local[slot]
+        else:
+            raise ValueError("mode must be 'p2p' or 'nccl'")
+        return dict(volume_mean=vol, count=count, valid=count.view(1, nx, ny, nz),
+                    view_range=(self.lg.begin, self.lg.end))
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, mode: str = "p2p", use_graph: bool = True) -> Dict[str, torch.Tensor]:
+        """One scene, everything on the current stream.  The returned tensors are views of
+        reused (p2p: peer-mapped) buffers: valid until the next-but-one forward; clone to keep."""
+        slot = self._slot
+        self._slot ^= 1
+        self._compute(slot, use_graph)
+        res = self._combine(slot, mode)
+        self._last_slot = slot
+        return res
+
+    def forward_stream(self, mode: str = "p2p", n_scenes: int = 8, use_graph: bool = True):
+        """A stream of ``n_scenes`` scenes (the resident scene replayed): the chain of scene i+1 runs
+        on the current stream while the combine of scene i runs on the communication stream."""
+        cur = torch.cuda.current_stream()
+        res = None
+        for _ in range(n_scenes):
+            slot = self._slot
+            self._slot ^= 1
+            if self._ev_free[slot] is not None:
+                cur.wait_event(self._ev_free[slot])          # the slot's partials were consumed
+            self._compute(slot, use_graph)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(self.s_comm):
+                self.s_comm.wait_event(ev)
+                res = self._combine(slot, mode)
+                done = torch.cuda.Event()
+                done.record(self.s_comm)
+            self._ev_free[slot] = done
+            self._last_slot = slot
+        cur.wait_stream(self.s_comm)
+        return res
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, g_volume_mean: torch.Tensor, g_variance: torch.Tensor):
+        """After ``forward`` (same slot): ``g_volume_mean`` [C,nx,ny,nz] (replicated on every rank),
+        ``g_variance`` logical [Vb,C,D,Hf,Wf] in channels_last_3d for this rank's reference views.
+        -> (g_feature [Vb,C,Hf,Wf] fp32 for the rank's own block, g_cost_out [Vb,2,D,Hf,Wf])."""
+        lib, cfg, lg, geo = self._lib, self.cfg, self.lg, self.lg.geo
+        dev = self.device
+        st = torch.cuda.current_stream().cuda_stream
+        vl, vb, c, n = self.vl, self.vb, self.c, self.n
+        d, t, k = cfg.num_depth, cfg.topk, geo.k
+        hf, wf = cfg.feat_hw
+        fdt = self._code(self.hot.feature_dtype)
+        if self._g_feat is None:
+            view_elems = hf * wf * c
+            # every rank allocates for the same (maximum) number of local views: symmetric allocation
+            vl_max = torch.tensor([vl], device=dev)
+            dist.all_reduce(vl_max, op=dist.ReduceOp.MAX, group=self.group)
+            self._g_feat = self._symm.empty(int(vl_max.item()) * view_elems, dtype=torch.float32, device=dev)
+            self._h_g = self._symm.rendezvous(self._g_feat, self.group)
+            offs, src = halo_pull_table(self.nbr_full, self.world, self.rank)
+            self._pull_offs, self._pull_src = offs.to(dev), src.to(dev)
+            self._n_pull = int(src.shape[0])
+            self.g_pn = torch.empty((vb, t, hf, wf), dtype=torch.float32, device=dev)
+            self.g_est_dens = torch.zeros((vb, t, hf, wf), dtype=torch.float32, device=dev)
+            self.g_cost_out = torch.empty((vb, 2, d, hf, wf), dtype=torch.float32, device=dev)
+            self.g_feature = torch.empty((vb, c, hf, wf), dtype=torch.float32, device=dev)
+        slot = self._last_slot
+        count = self.count_local[slot]
+        g_vol = g_volume_mean.reshape(c, n).float().contiguous()
+        gv = g_variance if g_variance.permute(0, 2, 3, 4, 1).is_contiguous() else \
+            g_variance.contiguous(memory_format=torch.channels_last_3d)
+        vdt = self._code(gv.dtype)
+        self._g_feat.zero_()
+        self.g_pn.zero_()
+        sv, s_t, sy, sx = self.est_depth.stride()
+        lib.call("mvsd_backproject_bwd", g_vol.data_ptr(), CHANNELS_FIRST, self._lib.BP_MEAN, count.data_ptr(),
+                 self.feat_cl.data_ptr(), fdt, hf, wf, geo.points.data_ptr(), geo.projection.data_ptr(),
+                 self.est_depth.data_ptr(), self.est_dens.data_ptr(), sv, sy, sx, s_t, float(cfg.voxel_size[2]),
+                 self._g_feat.data_ptr(), self.g_pn.data_ptr(), vb, c, geo.height, geo.width, t, n, st)
+        lib.call("mvsd_prob_norm_bwd", self.est_dens.data_ptr(), self.g_pn.data_ptr(), self.g_est_dens.data_ptr(),
+                 sv, sy, sx, s_t, vb, geo.height, geo.width, t, st)
+        sc = self.cost_out.stride()
+        lib.call("mvsd_depth_topk_bwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2], sc[4], self.est_idx.data_ptr(),
+                 None, None, None, self.g_est_dens.data_ptr(), None, None, 0, None, None,
+                 self.g_cost_out.data_ptr(), float(cfg.near_far_range[0]), float(cfg.depth_interval), 0,
+                 vb, d, hf, wf, t, st)
+        lib.call("mvsd_plane_sweep_bwd", gv.data_ptr(), vdt, CHANNELS_LAST, self.feat_cl.data_ptr(), fdt,
+                 lg.neighbor_ids_local.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(),
+                 self._g_feat.data_ptr(), vb, c, d, hf, wf, k, 0, vl, st)
+        # owners pull the halo contributions of their peers
+        self._h_g.barrier(channel=0)
+        if self._n_pull:
+            lib.call("mvsd_halo_reduce_p2p", self._h_g.buffer_ptrs_dev, self._pull_offs.data_ptr(),
+                     self._pull_src.data_ptr(), self.world, self.rank, vb, hf * wf * c, st)
+        self._h_g.barrier(channel=0)
+        lib.call("mvsd_unpack_nhwc_to_nchw", self._g_feat.data_ptr(), self.g_feature.data_ptr(), 0, vb, c, hf, wf, st)
+        return self.g_feature, self.g_cost_out
+
+    def close(self) -> None:
+        """Drop the captured graphs and peer-mapped buffers before the process group goes away."""
+        torch.cuda.synchronize(self.device)
+        self._graphs = [None, None]
+        self._g_feat = None

@@ -356,14 +356,17 @@ def test_warp_with_cameras_facing_away():
     sampled, mirrored); (b) q.z == 0 exactly on every pixel -> inf / NaN grid -> grid_sample adds
     nothing; (c) q.z tiny -> huge coordinates, outside.  Kernel == oracle (values and gradient)."""
     dv = torch.tensor([[0.5, 1.0, 2.0, 4.0]])
-    # (a) z = (0.08 x + 0.03 y - 0.6) d + 0.2 crosses zero within the 11 x 9 map for every plane
-    rot = torch.tensor([[[1.0, 0.02, 0.3], [-0.01, 1.0, -0.2], [0.08, 0.03, -0.6]]])
-    trans = torch.tensor([[0.1, -0.05, 0.2]])
+    # (a) rz = 0.2 x - 1.06 changes sign between x = 5 and x = 6; the other two rows are multiples of
+    # row 2 plus a small term, so px = 5 + (0.1 y + 0.2 + ..)/rz and py = 4 + (0.1 x + 0.3 + ..)/rz stay
+    # inside the 11 x 9 map on BOTH sides of the sign change
+    rot = torch.tensor([[[1.0, 0.1, -5.1], [0.9, 0.0, -3.94], [0.2, 0.0, -1.06]]])
+    trans = torch.tensor([[0.05, -0.03, 0.02]])
     want, got, gw, gg = _warp_pair(rot, trans, dv)
-    behind = float(((rot[0, 2, 0] * torch.arange(11.0)[None] + rot[0, 2, 1] * torch.arange(9.0)[:, None] + rot[0, 2, 2]) * 1.0
-                    + trans[0, 2] <= 0).float().mean())
-    assert 0.05 < behind < 0.95, "the case is supposed to mix q.z > 0 and q.z <= 0"
-    assert float(want.abs().max()) > 0
+    rz = 0.2 * torch.arange(11.0) - 1.06
+    assert bool((rz < 0).any()) and bool((rz > 0).any())
+    neg_cols = want[0, :, :, :, :5].abs().max()          # x <= 4: q.z < 0 for every plane (|tz| is small)
+    assert float(neg_cols) > 0, "samples behind the camera must still be taken (no z > 0 guard)"
+    assert float(want[0, :, :, :, 7:].abs().max()) > 0
     _close(got, want, "warp with q.z of both signs")
     _close(gg, gw, "warp backward with q.z of both signs")
     # (b) rot row 2 and trans z are zero: q.z == 0 everywhere (x/0 = +-inf, 0/0 = NaN)

@@ -115,3 +115,101 @@ def test_two_rank_gloo_allreduce_reproduces_whole_scene(case, tmp_path):
     # replicas are bit-identical after the all-reduce + identical normalisation
     assert np.array_equal(res[0]["mean"], res[1]["mean"])
     assert np.array_equal(res[0]["count"], res[1]["count"])
+
+
+def _ring_neighbours(v, k=2, seed=0):
+    """pose-neighbour-like ids: mostly adjacent views, a few long links"""
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for i in range(v):
+        cand = [(i + o) % v for o in (1, -1, 2, -2, 5)]
+        perm = torch.randperm(len(cand), generator=g).tolist()
+        rows.append([cand[p] for p in perm[:k]])
+    return torch.tensor(rows)
+
+
+@pytest.mark.parametrize("v,world", [(8, 2), (20, 3), (20, 4), (80, 8), (5, 8)])
+def test_halo_pull_table_reduces_to_the_whole_scene_gradient(v, world):
+    """Backward of the view-sharded scene (host logic of ShardedScenePipeline.backward): every rank
+    accumulates gradients for block + halo views; owners pull their peers' halo contributions
+    (sharded.halo_pull_table feeds mvsd_halo_reduce_p2p).  Emulated with CPU tensors: the
+    owner-side sums must equal the gradient of the unsharded scene."""
+    nbr = _ring_neighbours(v, seed=v)
+    e = 6
+    g = torch.Generator().manual_seed(1)
+    # contribution of reference view r to feature view n (itself and its neighbours)
+    contrib = {}
+    for r in range(v):
+        for n_ in [r] + nbr[r].tolist():
+            contrib[(r, n_)] = contrib.get((r, n_), 0) + torch.randn(e, generator=g, dtype=torch.float64)
+    whole = torch.zeros(v, e, dtype=torch.float64)
+    for (r, n_), val in contrib.items():
+        whole[n_] += val
+    # per-rank local accumulators over (block + halo) views
+    local, orders = [], []
+    for q in range(world):
+        b, en = sharded.partition_views(v, world, q)
+        if en <= b:
+            local.append(torch.zeros(0, e, dtype=torch.float64)); orders.append([])
+            continue
+        order, _ = sharded.halo_views(nbr[b:en], b, en)
+        buf = torch.zeros(len(order), e, dtype=torch.float64)
+        for (r, n_), val in contrib.items():
+            if b <= r < en:
+                buf[order.index(n_)] += val
+        local.append(buf); orders.append(order)
+    seen = 0
+    for q in range(world):
+        b, en = sharded.partition_views(v, world, q)
+        if en <= b:
+            continue
+        offs, src = sharded.halo_pull_table(nbr, world, q)
+        assert offs.dtype == torch.int32 and tuple(offs.shape) == (en - b + 1,)
+        mine = local[q][:en - b].clone()
+        for d_ in range(en - b):
+            for j in range(int(offs[d_]), int(offs[d_ + 1])):
+                peer, idx = int(src[j, 0]), int(src[j, 1])
+                assert peer != q and orders[peer][idx] == b + d_ and idx >= len(range(*sharded.partition_views(v, world, peer)))
+                mine[d_] += local[peer][idx]
+                seen += 1
+        assert torch.allclose(mine, whole[b:en], rtol=0, atol=1e-12)
+    total_halo = sum(max(0, len(o) - (sharded.partition_views(v, world, q)[1] - sharded.partition_views(v, world, q)[0]))
+                     for q, o in enumerate(orders))
+    assert seen == total_halo, "every halo view is pulled exactly once"
+
+
+def _worker_halo(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        v, e = 9, 5
+        nbr = _ring_neighbours(v, seed=4)
+        b, en = sharded.partition_views(v, world, rank)
+        order, _ = sharded.halo_views(nbr[b:en], b, en)
+        g = torch.Generator().manual_seed(100 + rank)
+        buf = torch.randn(len(order), e, generator=g, dtype=torch.float64)
+        # exchange the local buffers (what the peer pointers give the CUDA kernel)
+        bufs = [None] * world
+        dist.all_gather_object(bufs, (order, buf))
+        offs, src = sharded.halo_pull_table(nbr, world, rank)
+        mine = buf[:en - b].clone()
+        for d_ in range(en - b):
+            for j in range(int(offs[d_]), int(offs[d_ + 1])):
+                mine[d_] += bufs[int(src[j, 0])][1][int(src[j, 1])]
+        want = torch.zeros(en - b, e, dtype=torch.float64)
+        for q, (o, bq) in enumerate(bufs):
+            for i, gview in enumerate(o):
+                if b <= gview < en:
+                    want[gview - b] += bq[i]
+        np.savez(os.path.join(out_dir, f"halo{rank}.npz"), mine=mine.numpy(), want=want.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_halo_exchange(tmp_path):
+    world = 2
+    mp.spawn(_worker_halo, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        z = np.load(tmp_path / f"halo{r}.npz")
+        np.testing.assert_allclose(z["mine"], z["want"], rtol=0, atol=1e-12)

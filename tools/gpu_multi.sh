@@ -1,10 +1,9 @@
 #!/bin/bash
-# Multi-GPU sanity: scene-parallel bench (weak scaling) and the view-sharded test-time forward
-# (V=80) on N GPUs of one box.  N from $1 (default 2).  Outputs under gpurun_out/.
+# Multi-GPU round: 2-rank peer-memory tests, then the scene-parallel + view-sharded bench on N GPUs.
+#   tools/gpurun_retry.sh --gpus N 900 'bash tools/gpu_multi.sh N'
 N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/multi_smi.txt
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 300 --warmup 10 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
-cat gpurun_out/bench_n$N.json | cut -c1-400; tail -2 gpurun_out/bench_n$N.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29522 tools/run_sharded.py --views 80 --p2p > gpurun_out/sharded_v80_n$N.json 2> gpurun_out/sharded_v80_n$N.err
-cat gpurun_out/sharded_v80_n$N.json; tail -2 gpurun_out/sharded_v80_n$N.err
+timeout 300 python -m pytest tests/test_gpu_p2p.py -m gpu -x -q > gpurun_out/pytest_p2p.log 2>&1; tail -15 gpurun_out/pytest_p2p.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
+  bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+tail -c 3000 gpurun_out/bench_n$N.json; tail -5 gpurun_out/bench_n$N.err
