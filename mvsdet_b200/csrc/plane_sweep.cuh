@@ -74,16 +74,23 @@ __device__ __forceinline__ SweepCoord sweep_coord(const SweepParams& p, int warp
 
 // A neighbour id outside the feature tensor (stale or un-rebased ids against a compact / sliced
 // buffer) must neither be read nor -- in the backward -- be the target of a RED: such a
-// neighbour simply contributes no sample, like a warp that lands outside the map.
-__device__ __forceinline__ bool nbr_in_range(const SweepParams& p, int v, int j) {
-  if (p.nbr == nullptr) return true;              // stand-alone warp: source = same index
-  return (unsigned)__ldg(p.nbr + (size_t)v * p.k + j) < (unsigned)p.n_feat;
+// neighbour simply contributes no sample, like a warp that lands outside the map.  The check is
+// warp-uniform and made ONCE per warp (bit j of the mask = neighbour j usable) and parked in a
+// shared-memory word: the per-pixel sample fill reads it back as a broadcast.  (A dependent
+// global load inside the fill cost the forward 6 %; a live register cost the backward spills.)
+__device__ __forceinline__ unsigned nbr_ok_mask(const SweepParams& p, int v) {
+  if (p.nbr == nullptr) return 0xffffffffu;       // stand-alone warp: source = same index
+  unsigned m = 0u;
+  for (int j = 0; j < p.k; ++j)
+    m |= (unsigned)((unsigned)__ldg(p.nbr + (size_t)v * p.k + j) < (unsigned)p.n_feat) << j;
+  return m;
 }
 
 // One pass of sample geometry for this warp's pixel: lane s computes the sample
 // of (plane d0 + s / k, neighbour s % k).
 __device__ __forceinline__ void fill_samples(WarpSample* tab, const SweepParams& p,
-                                             const SweepCoord& c, int d0, int dc, int lane) {
+                                             const SweepCoord& c, int d0, int dc, int lane,
+                                             const unsigned* s_nbr_ok) {
   const int k = p.k;
   if (lane < dc * k) {
     const int dd = lane / k, j = lane - dd * k;
@@ -91,7 +98,7 @@ __device__ __forceinline__ void fill_samples(WarpSample* tab, const SweepParams&
     WarpSample s;
     s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
     s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
-    if (d < p.D && nbr_in_range(p, c.v, j)) {
+    if (d < p.D && ((*s_nbr_ok >> j) & 1u)) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
       float mm[12];
 #pragma unroll

@@ -22,9 +22,11 @@ __device__ __forceinline__ void red_tap(float* dst, unsigned off, const float4 (
 template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool WARP_ONLY>
 __global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepParams p) {
   __shared__ WarpSample s_tab[kSweepWarps][kSlots];
+  __shared__ unsigned s_nbr_ok[kSweepWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
   if (!c.ok) return;
+  if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);      // read after the __syncwarp() before each fill
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
   const unsigned pix = (unsigned)(c.y * p.W + c.x);
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepPar
   for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, dc, lane);
+      fill_samples(s_tab[warp], p, c, d0, dc, lane, &s_nbr_ok[warp]);
       __syncwarp();
     }
     const int dend = min(p.D, d0 + dc);

@@ -50,7 +50,8 @@ __device__ __forceinline__ RunCoord run_coord(const SweepParams& p, int warp, in
 
 // lane s -> sample (plane d0 + s / (kRun*k), pixel x0 + (s % (kRun*k)) / k, neighbour s % k)
 __device__ __forceinline__ void fill_run_samples(WarpSample* tab, const SweepParams& p,
-                                                 const RunCoord& c, int d0, int ppf, int lane) {
+                                                 const RunCoord& c, int d0, int ppf, int lane,
+                                                 const unsigned* s_nbr_ok) {
   const int k = p.k, spp = kRun * k;
   if (lane < ppf * spp) {
     const int dd = lane / spp, rem = lane - dd * spp;
@@ -59,7 +60,7 @@ __device__ __forceinline__ void fill_run_samples(WarpSample* tab, const SweepPar
     WarpSample s;
     s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
     s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
-    if (d < p.D && i < c.npix && nbr_in_range(p, c.v, j)) {
+    if (d < p.D && i < c.npix && ((*s_nbr_ok >> j) & 1u)) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
       float mm[12];
 #pragma unroll
@@ -238,10 +239,13 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
   constexpr int kCols = kRun * G * 4;
   __shared__ WarpSample s_tab[kRunRows][32];
   __shared__ uint32_t s_tmem;
+  __shared__ unsigned s_nbr_ok[kRunRows];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const RunCoord c = run_coord<G>(p, warp, lane);
   const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);
   if (c.y < p.H) {
+    if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);
+    __syncwarp();
     const int C = p.C, HW = p.H * p.W;
     const TIn* feat = static_cast<const TIn*>(p.feat);
     const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 
     for (int d0 = 0; d0 < p.D; d0 += ppf) {
       __syncwarp();
-      fill_run_samples(s_tab[warp], p, c, d0, ppf, lane);
+      fill_run_samples(s_tab[warp], p, c, d0, ppf, lane, &s_nbr_ok[warp]);
       __syncwarp();
       const int dend = min(p.D, d0 + ppf);
       for (int d = d0; d < dend; ++d) {
@@ -392,7 +396,8 @@ constexpr unsigned kHoSend = 1u, kHoRecv = 2u, kHoNzLeft = 4u, kHoNzRight = 8u;
 
 __device__ __forceinline__ void fill_run_samples_ho(WarpSample* tab, unsigned char* flg,
                                                     const SweepParams& p, const RunCoord& c, int d0,
-                                                    int ppf, int lane, bool has_up, bool has_dn) {
+                                                    int ppf, int lane, bool has_up, bool has_dn,
+                                                    const unsigned* s_nbr_ok) {
   const int k = p.k, spp = kRun * k;
   if (lane < ppf * spp) {
     const int dd = lane / spp, rem = lane - dd * spp;
@@ -402,7 +407,7 @@ __device__ __forceinline__ void fill_run_samples_ho(WarpSample* tab, unsigned ch
     s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
     s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
     unsigned f = 0u;
-    if (d < p.D && i < c.npix && nbr_in_range(p, c.v, j)) {
+    if (d < p.D && i < c.npix && ((*s_nbr_ok >> j) & 1u)) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
       float mm[12];
 #pragma unroll
@@ -602,6 +607,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
   // next planes, so the load pipeline never drains at a table refill
   __shared__ WarpSample s_tab[kRunRows][2][32];
   __shared__ unsigned char s_flg[kRunRows][2][32];
+  __shared__ unsigned s_nbr_ok[kRunRows];
   __shared__ __align__(8) unsigned long long s_bar[kRunRows - 1][KMAX][NSTG][2];   // {full, empty}
   __shared__ uint32_t s_tmem;
   static_assert(sizeof(WarpSample) == 32, "sample table stride");
@@ -613,6 +619,8 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
   }
   const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);     // contains the CTA barriers
   if (c.y < p.H) {
+    if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);
+    __syncwarp();
     const int C = p.C, HW = p.H * p.W;
     const TIn* feat = static_cast<const TIn*>(p.feat);
     const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
@@ -668,8 +676,8 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
     tmem_wait_st();
 
     PixelRaw<TIn, TG, G> raw;
-    fill_run_samples_ho(s_tab[warp][0], s_flg[warp][0], p, c, 0, ppf, lane, has_up, has_dn);
-    if (ppf < p.D) fill_run_samples_ho(s_tab[warp][1], s_flg[warp][1], p, c, ppf, ppf, lane, has_up, has_dn);
+    fill_run_samples_ho(s_tab[warp][0], s_flg[warp][0], p, c, 0, ppf, lane, has_up, has_dn, &s_nbr_ok[warp]);
+    if (ppf < p.D) fill_run_samples_ho(s_tab[warp][1], s_flg[warp][1], p, c, ppf, ppf, lane, has_up, has_dn, &s_nbr_ok[warp]);
     __syncwarp();
     // pipeline prologue: first pixel of the first plane
     issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp][0], g_d, ref_row, nsrc, c.c0, C);
@@ -726,7 +734,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
       // this buffer's planes are done (the loads already in flight read the other buffer): refill it
       __syncwarp();
       if (d0 + 2 * ppf < p.D)
-        fill_run_samples_ho(s_tab[warp][buf], s_flg[warp][buf], p, c, d0 + 2 * ppf, ppf, lane, has_up, has_dn);
+        fill_run_samples_ho(s_tab[warp][buf], s_flg[warp][buf], p, c, d0 + 2 * ppf, ppf, lane, has_up, has_dn, &s_nbr_ok[warp]);
       __syncwarp();
     }
     tmem_wait_st();

@@ -7,9 +7,11 @@ namespace mvsd {
 template <typename TIn, typename TOut, int KMAX, int G, bool FULL, bool WARP_ONLY>
 __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepParams p) {
   __shared__ WarpSample s_tab[kSweepWarps][kSlots];
+  __shared__ unsigned s_nbr_ok[kSweepWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
   if (!c.ok) return;                            // warps are independent: no CTA barrier below
+  if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);      // read after the __syncwarp() before each fill
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
   const unsigned pix = (unsigned)(c.y * p.W + c.x);
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
   for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, dc, lane);
+      fill_samples(s_tab[warp], p, c, d0, dc, lane, &s_nbr_ok[warp]);
       __syncwarp();
     }
     const int dend = min(p.D, d0 + dc);
@@ -93,9 +95,11 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
 template <typename TIn, typename TOut, int KMAX, int G, bool FULL>
 __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepParams p) {
   __shared__ WarpSample s_tab[kSweepWarps][kSlots];
+  __shared__ unsigned s_nbr_ok[kSweepWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
   if (!c.ok) return;
+  if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);      // read after the __syncwarp() before each fill
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
   const unsigned pix = (unsigned)(c.y * p.W + c.x);
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepP
   for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, dc, lane);
+      fill_samples(s_tab[warp], p, c, d0, dc, lane, &s_nbr_ok[warp]);
       __syncwarp();
     }
     const int dend = min(p.D, d0 + dc);

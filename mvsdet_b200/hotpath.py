@@ -126,7 +126,7 @@ class MVSDetHotPath(nn.Module):
         c = feat_cl.shape[1]
         volume_mean = vol.view(c, nx, ny, nz) if vol.is_contiguous() else vol.unflatten(1, (nx, ny, nz))
         out = dict(volume_mean=volume_mean, valid=count.view(1, nx, ny, nz).float(), count=count,
-                   variance=variance, prob_volume=prob, off_pred=off, est_depth=est_depth,
+                   variance=variance, cost_out=cost_out, prob_volume=prob, off_pred=off, est_depth=est_depth,
                    est_densities=est_dens, est_idx=est_idx,
                    # NVS branch: opacity = max_d prob_volume (mvsdet.py:579) is the top-1
                    # hypothesis probability, bit for bit

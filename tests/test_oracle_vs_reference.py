@@ -79,3 +79,35 @@ def test_geometry_mirrors_equal_live_reference(ref):
     pts = ref.get_points(n_voxels=torch.tensor(cfg.n_voxels), voxel_size=torch.tensor(cfg.voxel_size),
                          origin=torch.tensor(meta["lidar2img"]["origin"]))
     assert torch.equal(pts, G.get_points(cfg.n_voxels, cfg.voxel_size, meta["lidar2img"]["origin"]))
+
+
+def test_costreg_restatement_equals_reference_class():
+    """oracle/costreg_oracle.CostRegNet3DGS (what the GPU tests attach to the drop-in) against the
+    reference's CostRegNet_3DGS (mvs_models/mvsnet.py:73-113), loaded under a synthetic package
+    because mvsnet.py uses ``from .module import *``: same state_dict keys and shapes, same
+    output with the same weights."""
+    import sys
+    import types
+    from oracle import costreg_oracle
+    root = os.path.join(ref_loader.REFERENCE_ROOT, "projects", "NeRF-Det", "nerfdet", "mvs_models")
+    pkg = types.ModuleType("_ref_mvs_models")
+    pkg.__path__ = [root]
+    sys.modules["_ref_mvs_models"] = pkg
+    for name in ("module", "mvsnet"):
+        spec = importlib.util.spec_from_file_location(f"_ref_mvs_models.{name}", os.path.join(root, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+    torch.manual_seed(0)
+    theirs = sys.modules["_ref_mvs_models.mvsnet"].CostRegNet_3DGS()
+    mine = costreg_oracle.CostRegNet3DGS()
+    sd = theirs.state_dict()
+    assert list(sd.keys()) == list(mine.state_dict().keys())
+    assert all(sd[k].shape == v.shape for k, v in mine.state_dict().items())
+    assert sum(p.numel() for p in mine.parameters()) == 4871554          # SURVEY.md 8c
+    mine.load_state_dict(sd)
+    x = torch.randn(1, 256, 4, 8, 8)
+    for train in (False, True):
+        theirs.train(train)
+        mine.train(train)
+        assert torch.equal(theirs(x.clone()), mine(x.clone()))
