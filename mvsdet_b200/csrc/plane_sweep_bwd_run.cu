@@ -24,7 +24,10 @@
 namespace mvsd {
 
 constexpr int kRun = 8;                    // pixels per warp run
-constexpr int kRunQMinBlocks = 3;          // CTAs per SM the kernels are compiled for (168 registers)
+#ifndef MVSD_EXP_BWD_MINB
+#define MVSD_EXP_BWD_MINB 3
+#endif
+constexpr int kRunQMinBlocks = MVSD_EXP_BWD_MINB;   // CTAs per SM the kernels are compiled for (3: 168 registers)
 constexpr int kRunRows = 4;                // rows (= warps) per CTA
 constexpr int kRunThreads = kRunRows * 32;
 constexpr unsigned kNoTap = 0xfffffffeu;   // "nothing pending"
@@ -60,13 +63,13 @@ __device__ __forceinline__ void fill_run_samples(WarpSample* tab, const SweepPar
     WarpSample s;
     s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
     s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
-    if (d < p.D && i < c.npix && ((*s_nbr_ok >> j) & 1u)) {
+    if (d < p.D && i < c.npix) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
       float mm[12];
 #pragma unroll
       for (int t = 0; t < 12; ++t) mm[t] = __ldg(m + t);
-      s = make_warp_sample(mm, (float)(c.x0 + i), (float)c.y, __ldg(p.depth + (size_t)c.v * p.D + d),
-                           p.H, p.W, p.C);
+      s = make_warp_sample(mm, (float)(c.x0 + i), (float)c.y,
+                           depth_or_nan(__ldg(p.depth + (size_t)c.v * p.D + d), j, s_nbr_ok), p.H, p.W, p.C);
     }
     tab[lane] = s;
   }
@@ -244,8 +247,6 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
   const RunCoord c = run_coord<G>(p, warp, lane);
   const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);
   if (c.y < p.H) {
-    if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);
-    __syncwarp();
     const int C = p.C, HW = p.H * p.W;
     const TIn* feat = static_cast<const TIn*>(p.feat);
     const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
@@ -272,12 +273,18 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 
     const TIn* nsrc[KMAX];
     float* ndst[KMAX];
+    {
+      unsigned nbr_ok = 0u;
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
-      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
-      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
-      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+      for (int j = 0; j < KMAX; ++j) {
+        const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+        nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
+        nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+        ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+        asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+      }
+      if (lane == 0) s_nbr_ok[warp] = nbr_ok;     // read by the sample fills below
+      __syncwarp();
     }
     const float inv_n = 1.0f / (float)(KMAX + 1);
     const u64 inv_n2 = pk2(inv_n, inv_n);
@@ -407,12 +414,12 @@ __device__ __forceinline__ void fill_run_samples_ho(WarpSample* tab, unsigned ch
     s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
     s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
     unsigned f = 0u;
-    if (d < p.D && i < c.npix && ((*s_nbr_ok >> j) & 1u)) {
+    if (d < p.D && i < c.npix) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
       float mm[12];
 #pragma unroll
       for (int t = 0; t < 12; ++t) mm[t] = __ldg(m + t);
-      const float depth = __ldg(p.depth + (size_t)c.v * p.D + d);
+      const float depth = depth_or_nan(__ldg(p.depth + (size_t)c.v * p.D + d), j, s_nbr_ok);
       const float x = (float)(c.x0 + i);
       s = make_warp_sample(mm, x, (float)c.y, depth, p.H, p.W, p.C);
       if (s.p00 != kNoSample) {
@@ -619,8 +626,6 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
   }
   const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);     // contains the CTA barriers
   if (c.y < p.H) {
-    if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);
-    __syncwarp();
     const int C = p.C, HW = p.H * p.W;
     const TIn* feat = static_cast<const TIn*>(p.feat);
     const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
@@ -647,12 +652,18 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
 
     const TIn* nsrc[KMAX];
     float* ndst[KMAX];
+    {
+      unsigned nbr_ok = 0u;
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
-      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
-      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
-      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+      for (int j = 0; j < KMAX; ++j) {
+        const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+        nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
+        nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+        ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+        asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
+      }
+      if (lane == 0) s_nbr_ok[warp] = nbr_ok;     // read by the sample fills below
+      __syncwarp();
     }
     const float inv_n = 1.0f / (float)(KMAX + 1);
     const u64 inv_n2 = pk2(inv_n, inv_n);
@@ -756,7 +767,11 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
 // instead of 44 and the pipelined kernel spills (ptxas: 160 B of stack).
 template <typename TIn, typename TG>
 static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
+#ifdef MVSD_EXP_BWD_G1
+  const int G = 1;                    // experiment: 128-channel warps (two channel slices for C = 256)
+#else
   const int G = sweep_groups(p.C);
+#endif
   p.tiles_x = (p.W + kRun - 1) / kRun;
   p.tiles_y = (p.H + kRunRows - 1) / kRunRows;
   p.slices = (p.C + 128 * G - 1) / (128 * G);

@@ -11,7 +11,6 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
   if (!c.ok) return;                            // warps are independent: no CTA barrier below
-  if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);      // read after the __syncwarp() before each fill
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
   const unsigned pix = (unsigned)(c.y * p.W + c.x);
@@ -27,12 +26,15 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
     ref2[g] = f4mul(ref[g], ref[g]);
   }
   const TIn* nsrc[KMAX];
+  unsigned nbr_ok = 0u;
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     int n = c.v + p.ref_begin;
     if (!WARP_ONLY && j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
+    nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
     nsrc[j] = feat + (size_t)n * HW * C + c.c0;
   }
+  if (lane == 0) s_nbr_ok[warp] = nbr_ok;        // read after the __syncwarp() before each fill
   const float inv_n = 1.0f / (float)(k + 1);
   const int dc = k > 0 ? kSlots / k : p.D;      // planes per geometry pass
 
@@ -99,7 +101,6 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepP
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
   if (!c.ok) return;
-  if (lane == 0) s_nbr_ok[warp] = nbr_ok_mask(p, c.v);      // read after the __syncwarp() before each fill
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
   const unsigned pix = (unsigned)(c.y * p.W + c.x);
@@ -115,13 +116,16 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepP
   }
   TOut* o = out_pix;
   const TIn* nsrc[KMAX];
+  unsigned nbr_ok = 0u;
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     int n = c.v + p.ref_begin;
     if (j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
+    nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
     nsrc[j] = feat + (size_t)n * HW * C + c.c0;
     asm volatile("" : "+l"(nsrc[j]));           // keep the base in registers (ptxas re-derives it per plane otherwise)
   }
+  if (lane == 0) s_nbr_ok[warp] = nbr_ok;        // read after the __syncwarp() before each fill
   const float inv_n = 1.0f / (float)(k + 1);
   const u64 inv_n2 = pk2(inv_n, inv_n);
   const int dc = k > 0 ? kSlots / k : p.D;
