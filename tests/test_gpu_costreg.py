@@ -97,4 +97,6 @@ def test_bf16_variance_handoff_runs(setup):
                           cost_regularization=lambda var: net_c(var.to(torch.bfloat16)).float(), stride=cfg.stride,
                           feature_dtype=torch.bfloat16)
     res32 = hot32(feat_c.detach(), scene["img_meta"])
-    assert _rel(res["variance"].float(), res32["variance"]) < 2e-2
+    a, b = res["variance"].float(), res32["variance"]
+    # a bf16 output is the fp32 value rounded to 8 significant bits: |a-b| <= 2^-8 |b| (+ denormal slack)
+    assert bool(((a - b).abs() <= 2.0 ** -8 * b.abs() + 1e-30).all())
