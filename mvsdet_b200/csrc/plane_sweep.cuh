@@ -74,25 +74,23 @@ __device__ __forceinline__ SweepCoord sweep_coord(const SweepParams& p, int warp
 
 // A neighbour id outside the feature tensor (stale or un-rebased ids against a compact / sliced
 // buffer) must neither be read nor -- in the backward -- be the target of a RED: such a
-// neighbour simply contributes no sample, like a warp that lands outside the map.  The check is
-// warp-uniform and made ONCE per warp, where the kernels load the ids anyway (bit j of the mask =
-// neighbour j usable), and parked in a
-// shared-memory word: the per-pixel sample fill reads it back as a broadcast and, for an unusable
-// neighbour, replaces the plane depth by NaN: q = r * NaN + t is NaN -> "no sample", through the
-// code path that already exists.  One select, no new branch and no extra load (a dependent global
-// load inside the fill cost the forward 6 %, a live mask register cost the backward spills).
-__device__ __forceinline__ float depth_or_nan(float depth, int j, const unsigned* s_nbr_ok) {
-  return ((*s_nbr_ok >> j) & 1u) ? depth : __int_as_float(0x7fc00000);
+// neighbour simply contributes no sample, like a warp that lands outside the map.  The lane that
+// computes a sample loads its neighbour's id TOGETHER with the homography (independent loads, one
+// wait) and replaces the plane depth by NaN when the id is unusable: q = r * NaN + t is NaN ->
+// "no sample" through the code path that already exists.  One select, no branch on the loaded id
+// (a branch serialised the loads and cost the forward 6 %; a mask handed over through shared
+// memory put the id load in front of the fill, same cost).
+__device__ __forceinline__ int nbr_id_for_check(const SweepParams& p, int v, int j) {
+  return p.nbr ? __ldg(p.nbr + (size_t)v * p.k + j) : 0;      // stand-alone warp: no ids, always usable
 }
-__device__ __forceinline__ unsigned nbr_ok_bit(int n, int j, int n_feat) {
-  return (unsigned)((unsigned)n < (unsigned)n_feat) << j;
+__device__ __forceinline__ float depth_or_nan(float depth, int n, int n_feat) {
+  return (unsigned)n < (unsigned)n_feat ? depth : __int_as_float(0x7fc00000);
 }
 
 // One pass of sample geometry for this warp's pixel: lane s computes the sample
 // of (plane d0 + s / k, neighbour s % k).
 __device__ __forceinline__ void fill_samples(WarpSample* tab, const SweepParams& p,
-                                             const SweepCoord& c, int d0, int dc, int lane,
-                                             const unsigned* s_nbr_ok) {
+                                             const SweepCoord& c, int d0, int dc, int lane) {
   const int k = p.k;
   if (lane < dc * k) {
     const int dd = lane / k, j = lane - dd * k;
@@ -102,12 +100,13 @@ __device__ __forceinline__ void fill_samples(WarpSample* tab, const SweepParams&
     s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
     if (d < p.D) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
+      const int n = nbr_id_for_check(p, c.v, j);
       float mm[12];
 #pragma unroll
       for (int t = 0; t < 12; ++t) mm[t] = __ldg(m + t);
       const size_t di = (size_t)c.v * p.D + d;
       const float depth = p.depth_per_pixel ? __ldg(p.depth + (di * p.H + c.y) * p.W + c.x) : __ldg(p.depth + di);
-      s = make_warp_sample(mm, (float)c.x, (float)c.y, depth_or_nan(depth, j, s_nbr_ok), p.H, p.W, p.C);
+      s = make_warp_sample(mm, (float)c.x, (float)c.y, depth_or_nan(depth, n, p.n_feat), p.H, p.W, p.C);
     }
     tab[lane] = s;
   }

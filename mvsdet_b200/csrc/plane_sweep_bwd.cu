@@ -22,7 +22,6 @@ __device__ __forceinline__ void red_tap(float* dst, unsigned off, const float4 (
 template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool WARP_ONLY>
 __global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepParams p) {
   __shared__ WarpSample s_tab[kSweepWarps][kSlots];
-  __shared__ unsigned s_nbr_ok[kSweepWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
   if (!c.ok) return;
@@ -41,17 +40,14 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepPar
     if (!WARP_ONLY && group_on<FULL>(c.c0, g, C)) ref[g] = Io<TIn>::ld(feat + ref_off + 128 * g);
   }
   const TIn* nsrc[KMAX];
-  unsigned nbr_ok = 0u;
   float* ndst[KMAX];
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     int n = c.v + p.ref_begin;
     if (!WARP_ONLY && j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
-    nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
     nsrc[j] = feat + (size_t)n * HW * C + c.c0;
     ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
   }
-  if (lane == 0) s_nbr_ok[warp] = nbr_ok;        // read after the __syncwarp() before each fill
   const float inv_n = 1.0f / (float)(k + 1);
   const float two_inv_n = 2.0f * inv_n;
   const int dc = k > 0 ? kSlots / k : p.D;
@@ -59,7 +55,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepPar
   for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, dc, lane, &s_nbr_ok[warp]);
+      fill_samples(s_tab[warp], p, c, d0, dc, lane);
       __syncwarp();
     }
     const int dend = min(p.D, d0 + dc);

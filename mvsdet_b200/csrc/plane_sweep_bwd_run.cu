@@ -53,8 +53,7 @@ __device__ __forceinline__ RunCoord run_coord(const SweepParams& p, int warp, in
 
 // lane s -> sample (plane d0 + s / (kRun*k), pixel x0 + (s % (kRun*k)) / k, neighbour s % k)
 __device__ __forceinline__ void fill_run_samples(WarpSample* tab, const SweepParams& p,
-                                                 const RunCoord& c, int d0, int ppf, int lane,
-                                                 const unsigned* s_nbr_ok) {
+                                                 const RunCoord& c, int d0, int ppf, int lane) {
   const int k = p.k, spp = kRun * k;
   if (lane < ppf * spp) {
     const int dd = lane / spp, rem = lane - dd * spp;
@@ -65,11 +64,12 @@ __device__ __forceinline__ void fill_run_samples(WarpSample* tab, const SweepPar
     s.p00 = s.p01 = s.p10 = s.p11 = kNoSample;
     if (d < p.D && i < c.npix) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
+      const int n = nbr_id_for_check(p, c.v, j);
       float mm[12];
 #pragma unroll
       for (int t = 0; t < 12; ++t) mm[t] = __ldg(m + t);
       s = make_warp_sample(mm, (float)(c.x0 + i), (float)c.y,
-                           depth_or_nan(__ldg(p.depth + (size_t)c.v * p.D + d), j, s_nbr_ok), p.H, p.W, p.C);
+                           depth_or_nan(__ldg(p.depth + (size_t)c.v * p.D + d), n, p.n_feat), p.H, p.W, p.C);
     }
     tab[lane] = s;
   }
@@ -242,7 +242,6 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
   constexpr int kCols = kRun * G * 4;
   __shared__ WarpSample s_tab[kRunRows][32];
   __shared__ uint32_t s_tmem;
-  __shared__ unsigned s_nbr_ok[kRunRows];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const RunCoord c = run_coord<G>(p, warp, lane);
   const uint32_t tbase = tmem_alloc_cta<kCols>(&s_tmem, warp);
@@ -273,18 +272,12 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 
     const TIn* nsrc[KMAX];
     float* ndst[KMAX];
-    {
-      unsigned nbr_ok = 0u;
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
-        nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
-        nsrc[j] = feat + (size_t)n * HW * C + c.c0;
-        ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
-        asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
-      }
-      if (lane == 0) s_nbr_ok[warp] = nbr_ok;     // read by the sample fills below
-      __syncwarp();
+    for (int j = 0; j < KMAX; ++j) {
+      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
     }
     const float inv_n = 1.0f / (float)(KMAX + 1);
     const u64 inv_n2 = pk2(inv_n, inv_n);
@@ -298,7 +291,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runq_kernel(const
 
     for (int d0 = 0; d0 < p.D; d0 += ppf) {
       __syncwarp();
-      fill_run_samples(s_tab[warp], p, c, d0, ppf, lane, &s_nbr_ok[warp]);
+      fill_run_samples(s_tab[warp], p, c, d0, ppf, lane);
       __syncwarp();
       const int dend = min(p.D, d0 + ppf);
       for (int d = d0; d < dend; ++d) {
@@ -403,8 +396,7 @@ constexpr unsigned kHoSend = 1u, kHoRecv = 2u, kHoNzLeft = 4u, kHoNzRight = 8u;
 
 __device__ __forceinline__ void fill_run_samples_ho(WarpSample* tab, unsigned char* flg,
                                                     const SweepParams& p, const RunCoord& c, int d0,
-                                                    int ppf, int lane, bool has_up, bool has_dn,
-                                                    const unsigned* s_nbr_ok) {
+                                                    int ppf, int lane, bool has_up, bool has_dn) {
   const int k = p.k, spp = kRun * k;
   if (lane < ppf * spp) {
     const int dd = lane / spp, rem = lane - dd * spp;
@@ -416,10 +408,11 @@ __device__ __forceinline__ void fill_run_samples_ho(WarpSample* tab, unsigned ch
     unsigned f = 0u;
     if (d < p.D && i < c.npix) {
       const float* m = p.hom + ((size_t)c.v * k + j) * 12;
+      const int n = nbr_id_for_check(p, c.v, j);
       float mm[12];
 #pragma unroll
       for (int t = 0; t < 12; ++t) mm[t] = __ldg(m + t);
-      const float depth = depth_or_nan(__ldg(p.depth + (size_t)c.v * p.D + d), j, s_nbr_ok);
+      const float depth = depth_or_nan(__ldg(p.depth + (size_t)c.v * p.D + d), n, p.n_feat);
       const float x = (float)(c.x0 + i);
       s = make_warp_sample(mm, x, (float)c.y, depth, p.H, p.W, p.C);
       if (s.p00 != kNoSample) {
@@ -614,7 +607,6 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
   // next planes, so the load pipeline never drains at a table refill
   __shared__ WarpSample s_tab[kRunRows][2][32];
   __shared__ unsigned char s_flg[kRunRows][2][32];
-  __shared__ unsigned s_nbr_ok[kRunRows];
   __shared__ __align__(8) unsigned long long s_bar[kRunRows - 1][KMAX][NSTG][2];   // {full, empty}
   __shared__ uint32_t s_tmem;
   static_assert(sizeof(WarpSample) == 32, "sample table stride");
@@ -652,18 +644,12 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
 
     const TIn* nsrc[KMAX];
     float* ndst[KMAX];
-    {
-      unsigned nbr_ok = 0u;
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
-        nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
-        nsrc[j] = feat + (size_t)n * HW * C + c.c0;
-        ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
-        asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
-      }
-      if (lane == 0) s_nbr_ok[warp] = nbr_ok;     // read by the sample fills below
-      __syncwarp();
+    for (int j = 0; j < KMAX; ++j) {
+      const int n = __ldg(p.nbr + (size_t)c.v * KMAX + j);
+      nsrc[j] = feat + (size_t)n * HW * C + c.c0;
+      ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+      asm volatile("" : "+l"(nsrc[j]), "+l"(ndst[j]));
     }
     const float inv_n = 1.0f / (float)(KMAX + 1);
     const u64 inv_n2 = pk2(inv_n, inv_n);
@@ -687,8 +673,8 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
     tmem_wait_st();
 
     PixelRaw<TIn, TG, G> raw;
-    fill_run_samples_ho(s_tab[warp][0], s_flg[warp][0], p, c, 0, ppf, lane, has_up, has_dn, &s_nbr_ok[warp]);
-    if (ppf < p.D) fill_run_samples_ho(s_tab[warp][1], s_flg[warp][1], p, c, ppf, ppf, lane, has_up, has_dn, &s_nbr_ok[warp]);
+    fill_run_samples_ho(s_tab[warp][0], s_flg[warp][0], p, c, 0, ppf, lane, has_up, has_dn);
+    if (ppf < p.D) fill_run_samples_ho(s_tab[warp][1], s_flg[warp][1], p, c, ppf, ppf, lane, has_up, has_dn);
     __syncwarp();
     // pipeline prologue: first pixel of the first plane
     issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp][0], g_d, ref_row, nsrc, c.c0, C);
@@ -745,7 +731,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
       // this buffer's planes are done (the loads already in flight read the other buffer): refill it
       __syncwarp();
       if (d0 + 2 * ppf < p.D)
-        fill_run_samples_ho(s_tab[warp][buf], s_flg[warp][buf], p, c, d0 + 2 * ppf, ppf, lane, has_up, has_dn, &s_nbr_ok[warp]);
+        fill_run_samples_ho(s_tab[warp][buf], s_flg[warp][buf], p, c, d0 + 2 * ppf, ppf, lane, has_up, has_dn);
       __syncwarp();
     }
     tmem_wait_st();

@@ -7,7 +7,6 @@ namespace mvsd {
 template <typename TIn, typename TOut, int KMAX, int G, bool FULL, bool WARP_ONLY>
 __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepParams p) {
   __shared__ WarpSample s_tab[kSweepWarps][kSlots];
-  __shared__ unsigned s_nbr_ok[kSweepWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
   if (!c.ok) return;                            // warps are independent: no CTA barrier below
@@ -26,22 +25,19 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
     ref2[g] = f4mul(ref[g], ref[g]);
   }
   const TIn* nsrc[KMAX];
-  unsigned nbr_ok = 0u;
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     int n = c.v + p.ref_begin;
     if (!WARP_ONLY && j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
-    nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
     nsrc[j] = feat + (size_t)n * HW * C + c.c0;
   }
-  if (lane == 0) s_nbr_ok[warp] = nbr_ok;        // read after the __syncwarp() before each fill
   const float inv_n = 1.0f / (float)(k + 1);
   const int dc = k > 0 ? kSlots / k : p.D;      // planes per geometry pass
 
   for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, dc, lane, &s_nbr_ok[warp]);
+      fill_samples(s_tab[warp], p, c, d0, dc, lane);
       __syncwarp();
     }
     const int dend = min(p.D, d0 + dc);
@@ -97,7 +93,6 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
 template <typename TIn, typename TOut, int KMAX, int G, bool FULL>
 __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepParams p) {
   __shared__ WarpSample s_tab[kSweepWarps][kSlots];
-  __shared__ unsigned s_nbr_ok[kSweepWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
   if (!c.ok) return;
@@ -116,16 +111,13 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepP
   }
   TOut* o = out_pix;
   const TIn* nsrc[KMAX];
-  unsigned nbr_ok = 0u;
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     int n = c.v + p.ref_begin;
     if (j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
-    nbr_ok |= nbr_ok_bit(n, j, p.n_feat);
     nsrc[j] = feat + (size_t)n * HW * C + c.c0;
     asm volatile("" : "+l"(nsrc[j]));           // keep the base in registers (ptxas re-derives it per plane otherwise)
   }
-  if (lane == 0) s_nbr_ok[warp] = nbr_ok;        // read after the __syncwarp() before each fill
   const float inv_n = 1.0f / (float)(k + 1);
   const u64 inv_n2 = pk2(inv_n, inv_n);
   const int dc = k > 0 ? kSlots / k : p.D;
@@ -133,7 +125,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepP
   for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, dc, lane, &s_nbr_ok[warp]);
+      fill_samples(s_tab[warp], p, c, d0, dc, lane);
       __syncwarp();
     }
     const int dend = min(p.D, d0 + dc);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel CUDA-event medians of the benchmark step for the library selected by MVSDET_B200_LIB
 (experiment builds, tools/build_exp_lib.py), plus the graph-replayed step time and a checksum of
-g_feature against the first run's reference file (gpurun_out/time_kernels_ref.pt).
+g_feature against the first run of the same gpurun call (kept under /tmp).
 
     MVSDET_B200_LIB=mvsdet_b200/lib/exp_g1mb4.so python tools/time_kernels.py [--feature-dtype bf16]
 """
@@ -53,13 +53,12 @@ def main():
     torch.cuda.synchronize()
     out = {"lib": a.tag, "feature_dtype": a.feature_dtype, "step_ms_graph": round(e0.elapsed_time(e1) / 100, 4),
            "kernels_ms": ms}
-    ref_path = os.path.join(ROOT, "gpurun_out", f"time_kernels_ref_{a.feature_dtype}.pt")
+    ref_path = f"/tmp/time_kernels_ref_{a.feature_dtype}.pt"     # lives for one gpurun call
     g = pipes[0].g_feature.double().cpu()
     if os.path.isfile(ref_path):
         ref = torch.load(ref_path)
         out["g_feature_max_err_vs_ref_over_rms"] = float((g - ref).abs().max() / ref.pow(2).mean().sqrt())
     else:
-        os.makedirs(os.path.dirname(ref_path), exist_ok=True)
         torch.save(g, ref_path)
     print(json.dumps(out), flush=True)
 
