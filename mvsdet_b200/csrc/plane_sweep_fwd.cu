@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
   for (int d0 = 0; d0 < p.D; d0 += dc) {
     if (k > 0) {
       __syncwarp();
-      fill_samples(s_tab[warp], p, c, d0, dc, lane);
+      fill_samples<WARP_ONLY>(s_tab[warp], p, c, d0, dc, lane);
       __syncwarp();
     }
     const int dend = min(p.D, d0 + dc);
