@@ -53,6 +53,27 @@ def main():
     torch.cuda.synchronize()
     out = {"lib": a.tag, "feature_dtype": a.feature_dtype, "step_ms_graph": round(e0.elapsed_time(e1) / 100, 4),
            "kernels_ms": ms}
+    # two scenes in flight: both pipelines' steps forked inside ONE graph (tails of one scene's
+    # kernels are filled by the other's)
+    s_b = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    pair = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(pair):
+        cur = torch.cuda.current_stream()
+        s_b.wait_stream(cur)
+        pipes[0].step()
+        with torch.cuda.stream(s_b):
+            pipes[1].step()
+        cur.wait_stream(s_b)
+    for i in range(4):
+        pair.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(50):
+        pair.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    out["step_ms_two_in_flight"] = round(e0.elapsed_time(e1) / 100, 4)
     ref_path = f"/tmp/time_kernels_ref_{a.feature_dtype}.pt"     # lives for one gpurun call
     g = pipes[0].g_feature.double().cpu()
     if os.path.isfile(ref_path):
