@@ -17,17 +17,15 @@
 //   sweep_bwd_runq   lean column-merging kernel without hand-off; fp32 features
 //                    (the pipelined kernel spills with 80 raw-load registers per pixel)
 // The measured-and-dropped variants (scalar math, shared-memory accumulators, block / row-block
-// merging, deeper queues, L1 prefetch, pending taps in TMEM at 4 CTAs/SM) are in the git
-// history and in DESIGN.md section 5/8; they are not shipped.
+// merging, deeper queues, L1 prefetch, pending taps in TMEM at 4 CTAs/SM, 128-channel warps at
+// 4-5 CTAs/SM, producer / consumer warp specialisation over a shared-memory ring) are in the git
+// history, DESIGN.md section 5/8 and profiles/r02_bwd_experiments.md; they are not shipped.
 #include "plane_sweep.cuh"
 
 namespace mvsd {
 
 constexpr int kRun = 8;                    // pixels per warp run
-#ifndef MVSD_EXP_BWD_MINB
-#define MVSD_EXP_BWD_MINB 3
-#endif
-constexpr int kRunQMinBlocks = MVSD_EXP_BWD_MINB;   // CTAs per SM the kernels are compiled for (3: 168 registers)
+constexpr int kRunQMinBlocks = 3;          // CTAs per SM the kernels are compiled for (168 registers)
 constexpr int kRunRows = 4;                // rows (= warps) per CTA
 constexpr int kRunThreads = kRunRows * 32;
 constexpr unsigned kNoTap = 0xfffffffeu;   // "nothing pending"
@@ -753,11 +751,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
 // instead of 44 and the pipelined kernel spills (ptxas: 160 B of stack).
 template <typename TIn, typename TG>
 static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
-#ifdef MVSD_EXP_BWD_G1
-  const int G = 1;                    // experiment: 128-channel warps (two channel slices for C = 256)
-#else
   const int G = sweep_groups(p.C);
-#endif
   p.tiles_x = (p.W + kRun - 1) / kRun;
   p.tiles_y = (p.H + kRunRows - 1) / kRunRows;
   p.slices = (p.C + 128 * G - 1) / (128 * G);

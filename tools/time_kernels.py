@@ -25,9 +25,13 @@ def main():
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--feature-dtype", default="bf16")
     ap.add_argument("--tag", default=os.path.basename(os.environ.get("MVSDET_B200_LIB", "default")))
+    ap.add_argument("--tuning5", type=int, default=0, help="test hook mvsd_set_tuning(5, x) for the backward kernel")
     a = ap.parse_args()
     cfg = SceneConfig(n_views=20)
     dev = torch.device("cuda")
+    if a.tuning5:
+        from mvsdet_b200 import _lib
+        _lib.set_tuning(5, a.tuning5)
     mod = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk)
     pipes = []
     for b in range(2):
@@ -51,7 +55,7 @@ def main():
         graphs[i % 2].replay()
     e1.record()
     torch.cuda.synchronize()
-    out = {"lib": a.tag, "feature_dtype": a.feature_dtype, "step_ms_graph": round(e0.elapsed_time(e1) / 100, 4),
+    out = {"lib": a.tag, "tuning5": a.tuning5, "feature_dtype": a.feature_dtype, "step_ms_graph": round(e0.elapsed_time(e1) / 100, 4),
            "kernels_ms": ms}
     # two scenes in flight: both pipelines' steps forked inside ONE graph (tails of one scene's
     # kernels are filled by the other's)
