@@ -137,15 +137,11 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepP
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if (!group_on<FULL>(c.c0, g, C)) continue;
-          // var = S2/n - (S1/n)^2, every step rounded on its own (see the scalar kernel)
-          const float4 m = p4to(p4scale(s1[g], inv_n2));
-          const float4 q = p4to(p4scale(s2[g], inv_n2));
-          float4 r;
-          r.x = __fsub_rn(q.x, __fmul_rn(m.x, m.x));
-          r.y = __fsub_rn(q.y, __fmul_rn(m.y, m.y));
-          r.z = __fsub_rn(q.z, __fmul_rn(m.z, m.z));
-          r.w = __fsub_rn(q.w, __fmul_rn(m.w, m.w));
-          Io<TOut>::st_stream(o + 128 * g, r);
+          // var = S2/n - (S1/n)^2, every step rounded on its own (see the scalar kernel): mul.rn.f32x2 /
+          // sub.rn.f32x2 round each element exactly like the scalar _rn intrinsics, no contraction
+          const P4 m = p4scale(s1[g], inv_n2);
+          const P4 q = p4scale(s2[g], inv_n2);
+          Io<TOut>::st_stream(o + 128 * g, p4to(p4sub(q, p4mul(m, m))));
         }
       };
       if (KMAX <= 2) {

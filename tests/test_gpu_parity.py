@@ -240,9 +240,11 @@ def test_pack_unpack_roundtrip():
     assert torch.equal(out, x)
 
 
-@pytest.mark.parametrize("shape", [(2, 7, 5, 9), (1, 66, 13, 70), (3, 256, 60, 80)])
+@pytest.mark.parametrize("shape", [(2, 7, 5, 9), (1, 66, 13, 70), (3, 256, 60, 80), (2, 72, 6, 10), (1, 8, 2, 2),
+                                   (2, 132, 12, 16), (1, 64, 61, 4)])
 def test_pack_unpack_ragged_shapes(shape):
-    """64x64 transpose tiles: ragged channel / pixel edges, odd C, multi-tile maps."""
+    """64x64 transpose tiles: ragged channel / pixel edges, odd C, multi-tile maps; both the scalar
+    kernels (any shape) and the 16-byte kernels (HW % 4 == 0 and C % 8 == 0 / C % 4 == 0)."""
     from mvsdet_b200 import _lib
     v, c, h, w = shape
     x = torch.randn(*shape, device="cuda")
