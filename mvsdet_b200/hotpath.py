@@ -37,7 +37,7 @@ class MVSDetHotPath(nn.Module):
                  feature_dtype: torch.dtype = torch.float32,
                  variance_dtype: torch.dtype = torch.float32,
                  channels_first_volume: bool = True, num_neighbors: int = 2,
-                 dispatcher_ops: bool = False):
+                 dispatcher_ops: bool = False, strict_ncdhw_variance: bool = False):
         super().__init__()
         self.n_voxels = [int(n) for n in n_voxels]
         self.voxel_size = [float(s) for s in voxel_size]
@@ -55,6 +55,9 @@ class MVSDetHotPath(nn.Module):
         # True: go through the torch.library ops (torch.ops.mvsdet_b200.*, library.py) instead of
         # the autograd.Function layer -- same launchers, same kernels, traceable with fake tensors
         self.dispatcher_ops = bool(dispatcher_ops)
+        # True: hand the cost-regularisation net the variance in the reference's strict NCDHW
+        # contiguous memory (one extra transpose pass) instead of channels_last_3d
+        self.strict_ncdhw_variance = bool(strict_ncdhw_variance)
 
     def geometry(self, img_meta: dict, device, view_slice=None, prologue=None) -> SceneGeometry:
         """Per-scene parameter block (mvsdet.py:407-450).  ``prologue``: "device" (default: two
@@ -118,6 +121,8 @@ class MVSDetHotPath(nn.Module):
         if self.dispatcher_ops:
             sink = None
         variance = self.variance(feat_cl, geo, grad_sink=sink)
+        if self.strict_ncdhw_variance:
+            variance = ops.volume_to_ncdhw(variance)
         cost_out = cost_net(variance)
         hyp = self.hypotheses(cost_out, geo.k_feat if nvs else None)
         prob, off, est_depth, est_dens, est_idx, coding = hyp[:6]

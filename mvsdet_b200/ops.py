@@ -23,7 +23,7 @@ from ._lib import (BF16, BP_MEAN, BP_PER_VIEW, BP_SUM, CHANNELS_FIRST, CHANNELS_
 
 __all__ = ["pack_features", "plane_sweep_variance", "homo_warp", "depth_topk", "depth_topk_nvs",
            "topk_hypotheses", "ray_depth_scale", "rgb_downsample4", "backproject_aggregate",
-           "backproject_per_view", "voxel_normalize", "scene_setup"]
+           "backproject_per_view", "voxel_normalize", "scene_setup", "volume_to_ncdhw", "FeatureGradSink"]
 
 
 # --------------------------------------------------------------------------
@@ -189,6 +189,42 @@ def pack_features(x: torch.Tensor, dtype: torch.dtype = torch.float32, sink: boo
         return _PackFeaturesSink.apply(x, dtype, gs), gs
     out = _PackFeatures.apply(x, dtype)
     return (out, None) if sink else out
+
+
+class _VolumeToNCDHW(torch.autograd.Function):
+    """[V,C,D,H,W] logical volume in channels_last_3d memory -> the reference's strict NCDHW
+    contiguous memory (and back for the gradient), with the same transpose kernels as the feature
+    maps: a volume is a feature map with H' = D*H."""
+
+    @staticmethod
+    def forward(ctx, vol):
+        v, c, d, h, w = vol.shape
+        out = torch.empty((v, c, d, h, w), dtype=torch.float32, device=vol.device)
+        _lib.call("mvsd_unpack_nhwc_to_nchw", vol.data_ptr(), out.data_ptr(), 0, v, c, d * h, w, _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        v, c, d, h, w = g.shape
+        g = g.float().contiguous()
+        out = _empty_ndhwc(v, c, d, h, w, torch.float32, g.device)
+        _lib.call("mvsd_pack_nchw_to_nhwc", g.data_ptr(), out.data_ptr(), F32, v, c, d * h, w, _stream())
+        return out
+
+
+def volume_to_ncdhw(vol: torch.Tensor) -> torch.Tensor:
+    """The variance volume as the reference materialises it: [V,C,D,H,W] fp32 CONTIGUOUS
+    (mvsdet.py:439-467).  The kernels produce channels_last_3d, which cuDNN's Conv3d (the only
+    consumer, mvsnet.py:76) takes as is; a consumer that needs strict NCDHW memory pays one extra
+    transpose pass here (2.4 GB of traffic at the benchmark size, ~0.4 ms)."""
+    _need_cuda("volume", vol)
+    if vol.dim() != 5:
+        raise ValueError("volume must be [V,C,D,H,W]")
+    if vol.is_contiguous():
+        return vol
+    if vol.dtype != torch.float32 or not _is_ndhwc(vol):
+        raise ValueError("volume_to_ncdhw takes an fp32 channels_last_3d volume")
+    return _VolumeToNCDHW.apply(vol)
 
 
 # --------------------------------------------------------------------------
