@@ -40,7 +40,7 @@ WANT = [
 KERNEL_KEYS = (("sweep_fwd", "plane_sweep_fwd"), ("sweep_bwd", "plane_sweep_bwd"),
                ("backproject_fwd", "backproject_fwd"), ("backproject_bwd", "backproject_bwd"),
                ("depth_topk_fwd", "depth_topk_fwd"), ("depth_topk_bwd", "depth_topk_bwd"),
-               ("unpack_kernel", "unpack"), ("pack_kernel", "pack"), ("prob_norm", "prob_norm_bwd"))
+               ("unpack", "unpack"), ("pack", "pack"), ("prob_norm", "prob_norm_bwd"))    # unpack before pack
 
 
 def to_bytes(value, unit):

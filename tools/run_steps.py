@@ -1,12 +1,10 @@
 #!/usr/bin/env python
-"""Run a few un-graphed ScenePipeline steps (for ncu / compute-sanitizer) and
-optionally time kernel variants selected through mvsd_set_tuning.
+"""Run a few un-graphed ScenePipeline steps (for ncu / compute-sanitizer): every kernel of the
+benchmark step back to back on one stream, per-kernel CUDA-event means printed as JSON.
 
-    python tools/run_steps.py --steps 3
-    python tools/run_steps.py --sweep          # time tuning variants with CUDA events
+    python tools/run_steps.py --steps 3 [--feature-dtype f32]
 """
 import argparse
-import itertools
 import json
 import os
 import statistics
@@ -16,7 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from mvsdet_b200 import _lib  # noqa: E402
 from mvsdet_b200.hotpath import MVSDetHotPath  # noqa: E402
 from mvsdet_b200.pipeline import ScenePipeline  # noqa: E402
 from mvsdet_b200.scene import SceneConfig, make_scene  # noqa: E402
@@ -27,8 +24,6 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--views", type=int, default=20)
     ap.add_argument("--feature-dtype", default="bf16")
-    ap.add_argument("--sweep", action="store_true")
-    ap.add_argument("--tuning", default="", help="key=value,key=value")
     a = ap.parse_args()
     cfg = SceneConfig(n_views=a.views)
     dev = torch.device("cuda")
@@ -41,10 +36,6 @@ def main():
         p.set_geometry(mod.geometry(scene["img_meta"], dev))
         p.load_scene(scene)
         pipes.append(p)
-    for kv in filter(None, a.tuning.split(",")):
-        k, v = kv.split("=")
-        _lib.set_tuning(int(k), int(v))
-
     def timed(n):
         timers = {}
         for i in range(n):
@@ -52,24 +43,8 @@ def main():
         torch.cuda.synchronize()
         return {k: statistics.mean(x.elapsed_time(y) for x, y in v[1:]) for k, v in timers.items()}
 
-    if not a.sweep:
-        res = timed(a.steps)
-        print(json.dumps({k: round(v, 4) for k, v in res.items()}))
-        return
-    timed(3)
-    for ppw, pw in itertools.product((1, 2, 4), (2, 4, 8, 16)):
-        if (8 * ppw) % pw:
-            continue
-        _lib.set_tuning(0, ppw)
-        _lib.set_tuning(1, pw)
-        _lib.set_tuning(2, min(ppw, 2))
-        try:
-            r = timed(8)
-        except Exception as e:   # noqa: BLE001
-            print("ppw", ppw, "pw", pw, "failed", e)
-            continue
-        print(f"ppw={ppw} pw={pw} ph={8 * ppw // pw}: fwd {r['plane_sweep_fwd']:.4f} ms, "
-              f"bwd(ppw={min(ppw, 2)}) {r['plane_sweep_bwd']:.4f} ms", flush=True)
+    res = timed(a.steps)
+    print(json.dumps({k: round(v, 4) for k, v in res.items()}))
 
 
 if __name__ == "__main__":

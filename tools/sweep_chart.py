@@ -102,10 +102,10 @@ def main():
         grid = [(10, 16, 60, 80), (4, 64, 120, 160)]
     else:
         for hf, wf in ((60, 80), (120, 160)):
-            for d in (12, 16, 32, 64):
+            for d in (12, 16, 32, 48, 64):
                 for v in (10, 20, 50, 100):
                     grid.append((v, d, hf, wf))
-        for d in (16, 64):                                      # full-resolution 480x640 feature maps
+        for d in (16, 48, 64):                                  # full-resolution 480x640 feature maps
             grid.append((10, d, 480, 640))
     rows = []
     for v, d, hf, wf in grid:
