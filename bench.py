@@ -59,6 +59,35 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this rank's threads (and therefore the pages of its pinned host buffers, which are
+    first-touched by the allocating thread) to the NUMA node the GPU hangs off: with 8 ranks the
+    host <-> device copies of the e2e leg otherwise cross the socket interconnect.  Best effort:
+    returns the node id, or None when sysfs / nvidia-smi do not say."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not bdf:
+            return None
+        if len(bdf.split(":")[0]) == 8:                    # 00000000:1B:00.0 -> 0000:1b:00.0
+            bdf = bdf[4:]
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:                                      # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -386,6 +415,7 @@ def run_own_arm(args, cfg, cfg_json):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: mvsdet_b200 has no CPU path "
                            "(use --impl reference for the CPU baseline)")
+    numa_node = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -598,7 +628,7 @@ def run_own_arm(args, cfg, cfg_json):
                     "ms_per_step": ms_e2e / e2e_steps, "outputs_match_device": e2e_ok,
                     "overlap": "H2D / compute / D2H on three streams over %d buffer sets" % NBUF,
                     "ms_per_step_serial": ms_e2e_serial,
-                    "h2d_bytes_by_input": h2d_parts,
+                    "h2d_bytes_by_input": h2d_parts, "host_numa_node": numa_node,
                     "h2d_fraction_g_variance": round(h2d_parts["g_variance"] / p0.h2d_bytes(), 3),
                     "note": "g_variance (the gradient the cost-regularisation net returns) is 90 % of the "
                             "upload: on a real detector it is produced on the device; here it is a synthetic "
