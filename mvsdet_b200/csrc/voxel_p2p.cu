@@ -166,11 +166,12 @@ extern "C" int mvsd_voxel_reduce_p2p(const void* const* part_ptrs, void* const* 
   p2p_count_kernel<<<(N + 255) / 256, 256, 0, st>>>(p);
   count_launch();
   if (int e = check_launch("voxel_reduce_p2p(count)")) return e;
-  // one wave of 148 SMs x 8 CTAs: enough peer loads in flight to cover the NVLink round trip
+  // 148 SMs x 2 CTAs of 256 threads, each thread ~4 float4 per peer in flight: enough peer loads to
+  // cover the NVLink round trip without taking every SM slot from a sweep that runs concurrently
   const size_t total4 = ((size_t)C * N) >> 2;
   const size_t chunk = (total4 + world - 1) / world;
   const size_t want = (chunk + 255) / 256;
-  const unsigned blocks = (unsigned)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+  const unsigned blocks = (unsigned)(want < 148 * 2 ? (want ? want : 1) : 148 * 2);
   switch (world) {
     case 2: p2p_reduce_kernel<2><<<blocks, 256, 0, st>>>(p); break;
     case 4: p2p_reduce_kernel<4><<<blocks, 256, 0, st>>>(p); break;

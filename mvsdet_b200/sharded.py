@@ -367,7 +367,9 @@ class ShardedScenePipeline:
         self.h_out = [symm.rendezvous(t, self.group) for t in self.out]
         self.count_local = [torch.empty(self.n, dtype=torch.int32, device=dev) for _ in range(2)]
         self.nccl_out = [torch.empty(self.total, dtype=torch.float32, device=dev) for _ in range(2)]
-        self.s_comm = torch.cuda.Stream(device=dev)
+        # higher priority: the combine's barrier / reduce CTAs are dispatched as soon as SM slots free up,
+        # ahead of the next scene's queued sweep CTAs (at equal priority they wait for the sweep's last wave)
+        self.s_comm = torch.cuda.Stream(device=dev, priority=-1)
         self._ev_part = [None, None]      # partials of slot written (compute stream)
         self._ev_free = [None, None]      # slot's partial buffer consumed by the combine (comm stream)
         self._graphs = [None, None]
