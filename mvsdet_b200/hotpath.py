@@ -89,20 +89,24 @@ class MVSDetHotPath(nn.Module):
             return library.depth_topk(cost_out, self.near_far_range[0], self.depth_interval, self.topk)
         return ops.depth_topk(cost_out, self.near_far_range[0], self.depth_interval, self.topk)
 
-    def voxels(self, feat_cl, geo: SceneGeometry, est_depth, est_dens, mode: str = "mean", grad_sink=None):
-        if self.dispatcher_ops:
+    def voxels(self, feat_cl, geo: SceneGeometry, est_depth, est_dens, mode: str = "mean", grad_sink=None,
+               out=None, count_out=None):
+        if self.dispatcher_ops and out is None:
             return library.backproject_aggregate(feat_cl, geo.points, geo.projection, est_depth, est_dens,
                                                  self.voxel_size[2], geo.height, geo.width,
                                                  {"mean": False, "sum": True}[mode],
                                                  self.channels_first_volume)
         return ops.backproject_aggregate(feat_cl, geo.points, geo.projection, est_depth, est_dens,
                                          self.voxel_size[2], geo.height, geo.width, mode=mode,
-                                         channels_first=self.channels_first_volume, grad_sink=grad_sink)
+                                         channels_first=self.channels_first_volume, grad_sink=grad_sink,
+                                         out=out, count_out=count_out)
 
     # -- the whole block ---------------------------------------------------
     def forward(self, feature: torch.Tensor, img_meta: dict,
                 cost_regularization: Optional[Callable] = None,
-                geometry: Optional[SceneGeometry] = None, nvs: bool = False) -> Dict[str, torch.Tensor]:
+                geometry: Optional[SceneGeometry] = None, nvs: bool = False,
+                volume_out: Optional[torch.Tensor] = None,
+                count_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """feature [V,C,Hf,Wf] (fp32 NCHW as the reference's FPN gives it, or
         already channels_last / bf16).  Returns a dict with
           volume_mean [C,nx,ny,nz], valid [1,nx,ny,nz] (float count, as
@@ -126,7 +130,8 @@ class MVSDetHotPath(nn.Module):
         cost_out = cost_net(variance)
         hyp = self.hypotheses(cost_out, geo.k_feat if nvs else None)
         prob, off, est_depth, est_dens, est_idx, coding = hyp[:6]
-        vol, count = self.voxels(feat_cl, geo, est_depth, est_dens, grad_sink=sink)
+        vol, count = self.voxels(feat_cl, geo, est_depth, est_dens, grad_sink=sink, out=volume_out,
+                                 count_out=count_out)
         nx, ny, nz = self.n_voxels
         c = feat_cl.shape[1]
         volume_mean = vol.view(c, nx, ny, nz) if vol.is_contiguous() else vol.unflatten(1, (nx, ny, nz))
@@ -147,3 +152,46 @@ class MVSDetHotPath(nn.Module):
             out["est_ray_depth"] = ray_depth[:, :, :h, :w].reshape(v, self.topk, h * w).transpose(2, 1).unsqueeze(2)
             out["ray_depth_coding"] = ray_coding[:, :h, :w].reshape(v, h * w, 1)
         return out
+
+    def forward_batch(self, features, img_metas, cost_regularization: Optional[Callable] = None,
+                      nvs: bool = False):
+        """The scene loop of ``extract_feat`` (mvsdet.py:404-698) up to the neck: every scene's
+        volume is written by the back-projection kernel straight into its slot of the stacked
+        batch tensor (the reference appends to a list and ``torch.stack``s, :684-696 -- two extra
+        passes over 26 MB per scene).  -> (x [B,C,nx,ny,nz] -- the input of ``neck_3d`` --,
+        valids [B,1,nx,ny,nz] float counts as ``extract_feat`` returns them (:698), per-scene dicts)."""
+        if len(features) != len(img_metas) or not len(features):
+            raise ValueError("one img_meta per scene")
+        if not self.channels_first_volume:
+            raise ValueError("forward_batch stacks [C,nx,ny,nz] volumes: channels_first_volume=True")
+        b = len(features)
+        c = features[0].shape[1]
+        nx, ny, nz = self.n_voxels
+        dev = features[0].device
+        x = torch.empty((b, c, nx * ny * nz), dtype=torch.float32, device=dev)
+        counts = torch.empty((b, nx * ny * nz), dtype=torch.int32, device=dev)
+        outs, vols = [], []
+        for i, (feature, meta) in enumerate(zip(features, img_metas)):
+            out = self.forward(feature, meta, cost_regularization, nvs=nvs, volume_out=x[i], count_out=counts[i])
+            outs.append(out)
+            vols.append(out["volume_mean"])
+        xb = x.view(b, c, nx, ny, nz)
+        if any(v.requires_grad for v in vols):
+            # the kernels already wrote every scene into x: wire the scenes' autograd nodes behind
+            # the batch tensor without copying (the backward hands each scene its slice of the gradient)
+            xb = _StackFilled.apply(xb, *vols)
+        return xb, counts.view(b, 1, nx, ny, nz).float(), outs
+
+
+class _StackFilled(torch.autograd.Function):
+    """``torch.stack(vols)`` when ``filled`` already holds the stacked values (each vols[i] IS
+    filled[i]): forward returns the filled tensor, backward returns the per-scene gradient slices."""
+
+    @staticmethod
+    def forward(ctx, filled, *vols):
+        ctx.shapes = [tuple(v.shape) for v in vols]
+        return filled.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(g[i].reshape(shape) for i, shape in enumerate(ctx.shapes))

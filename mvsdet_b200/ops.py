@@ -620,17 +620,28 @@ def _bp_bwd_raw(g_out, feat, points, projection, est_depth, est_dens, count, vs_
     return g_feat, g_prob
 
 
+def ctx_count_is_external(count, out) -> bool:
+    """True when the back-projection wrote into caller-owned buffers (``out=`` / ``count_out=``)."""
+    return out is not None
+
+
 class _BackprojectAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, points, projection, est_depth, est_dens, vs_z, h, w, mode, channels_first,
                 out=None, count=None, sink=None):
+        external = out is not None or count is not None
         res, count = _bp_fwd_raw(feat, points, projection, est_depth, est_dens, vs_z, h, w, mode,
                                  channels_first, out, count)
-        # Only MEAN mode needs the count in its backward (s_u = 1/(count+1e-8)); SUM mode -- the
-        # only mode that accepts caller-owned (reused, peer-mapped) buffers -- saves nothing that
-        # aliases them, so a later call that overwrites the buffers cannot corrupt this graph.
-        ctx.save_for_backward(feat, points, projection, est_depth, est_dens,
-                              count if mode == BP_MEAN else None)
+        out = res if external else None
+        # Only MEAN mode needs the count in its backward (s_u = 1/(count+1e-8)); SUM mode saves
+        # nothing that aliases caller-owned (reused, peer-mapped) buffers, so a later call that
+        # overwrites them cannot corrupt this graph.
+        # With a caller-owned count buffer (a slice of a batch tensor, a peer-mapped buffer) the
+        # backward keeps its own copy (N int32 = 100 KB): a later writer cannot change s_u.
+        keep = None
+        if mode == BP_MEAN:
+            keep = count.clone() if ctx_count_is_external(count, out) else count
+        ctx.save_for_backward(feat, points, projection, est_depth, est_dens, keep)
         ctx.consts = (float(vs_z), h, w, mode, channels_first)
         ctx.sink = sink
         ctx.mark_non_differentiable(count)
@@ -670,9 +681,11 @@ def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: f
     The result is logical [C,N]; with channels_first=False its memory is [N,C]
     (channels_last_3d once viewed as [C,nx,ny,nz]).  ``out`` / ``count_out``: write into
     caller-owned buffers (memory order of the volume: [C,N] or [N,C] contiguous) -- the
-    view-sharded path lets the kernel write its partials straight into peer-mapped memory
-    (mode='sum' only; the buffers are overwritten in place without bumping autograd's version
-    counters, so hand the same buffers to a later call only after the result has been consumed)."""
+    view-sharded path lets the kernel write its partials straight into peer-mapped memory, the
+    batched drop-in lets it write each scene's volume into its slot of the stacked batch tensor
+    (mvsdet.py:695).  The buffers are overwritten in place without bumping autograd's version
+    counters; the backward keeps a private copy of the count, so reusing the buffers later cannot
+    corrupt this graph -- but the VALUES handed back are the buffers themselves."""
     _need_cuda("feat", feat)
     if not _is_nhwc(feat):
         raise ValueError("feat must be channels_last; use ops.pack_features")
@@ -690,9 +703,6 @@ def backproject_aggregate(feat, points, projection, est_depth, est_dens, vs_z: f
     m = {"mean": BP_MEAN, "sum": BP_SUM}[mode]
     if grad_sink is not None and grad_sink.shape != tuple(feat.shape):
         raise ValueError("grad_sink belongs to a different feature tensor")
-    if m == BP_MEAN and (out is not None or count_out is not None):
-        raise ValueError("caller-owned out / count_out buffers are for mode='sum' (the multi-GPU partials): "
-                         "in 'mean' mode the backward reads the count, which a reused buffer would clobber")
     return _BackprojectAggregate.apply(feat, points.contiguous().float(),
                                        projection.contiguous().float(), est_depth, est_dens,
                                        float(vs_z), int(height), int(width), m, bool(channels_first),

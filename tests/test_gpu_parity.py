@@ -452,3 +452,60 @@ def test_strict_ncdhw_variance_layout():
     _close(res["variance"], gold["variance"], "strict NCDHW variance")
     g, = torch.autograd.grad(res["variance"], feature, scene["g_variance"].to(dev))
     _close(g, gold["g_feature_from_variance"], "gradient through the NCDHW transpose")
+
+
+def test_forward_batch_writes_scenes_into_the_stacked_tensor():
+    """f4 hand-off (mvsdet.py:684-698): volumes of a batch of scenes land in one [B,C,nx,ny,nz]
+    tensor without a stack copy, valids as float counts; values and gradients equal the
+    scene-by-scene drop-in."""
+    from mvsdet_b200.hotpath import MVSDetHotPath
+    sa, ga = load_golden("scannet_tiny")
+    cfg = sa["cfg"]
+    from mvsdet_b200.scene import make_scene
+    sb = make_scene(cfg, seed=77)
+    dev = torch.device("cuda")
+    hot = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk, stride=cfg.stride)
+    feats = [s["feature"].to(dev).requires_grad_(True) for s in (sa, sb)]
+    costs = [s["cost_out"].to(dev) for s in (sa, sb)]
+    it = iter(costs)
+    x, valids, outs = hot.forward_batch(feats, [sa["img_meta"], sb["img_meta"]], cost_regularization=lambda var: next(it))
+    assert tuple(x.shape) == (2, cfg.channels, *cfg.n_voxels) and tuple(valids.shape) == (2, 1, *cfg.n_voxels)
+    assert valids.dtype == torch.float32
+    assert outs[0]["volume_mean"].data_ptr() == x[0].data_ptr(), "scene 0 must have been written in place"
+    _close(x[0], ga["volume_mean"], "batched volume 0")
+    assert np.array_equal(valids[0].cpu().numpy().astype(np.int64), ga["count"])
+    g = torch.randn(x.shape, generator=torch.Generator().manual_seed(1)).to(dev)
+    grads = torch.autograd.grad(x, feats, g)
+    # scene by scene
+    for i, s in enumerate((sa, sb)):
+        f = s["feature"].to(dev).requires_grad_(True)
+        res = hot(f, s["img_meta"], cost_regularization=lambda var: costs[i])
+        assert torch.equal(res["volume_mean"], x[i])
+        gi, = torch.autograd.grad(res["volume_mean"], f, g[i])
+        _close(grads[i], gi, f"batched gradient {i}", rtol=1e-5, atol_scale=1e-6)
+
+
+def test_backproject_sum_mode_channels_last():
+    """MVSD_BP_SUM with the [N,C] memory order (the multi-GPU partials in channels-last form):
+    sum == mean * (count + 1e-8) of the reference, counts bit-exact."""
+    from mvsdet_b200 import ops
+    scene, gold = load_golden("scannet_tiny")
+    cfg = scene["cfg"]
+    dev = torch.device("cuda")
+    mod = _module(cfg)
+    geo = mod.geometry(scene["img_meta"], dev)
+    feat = ops.pack_features(scene["feature"].to(dev), torch.float32)
+    est_depth = torch.from_numpy(gold["est_depth"]).to(dev)
+    est_dens = torch.from_numpy(gold["est_densities"]).to(dev)
+    outs = {}
+    for cf in (True, False):
+        vol, cnt = ops.backproject_aggregate(feat, geo.points, geo.projection, est_depth, est_dens,
+                                             cfg.voxel_size[2], geo.height, geo.width, mode="sum", channels_first=cf)
+        assert tuple(vol.shape) == (cfg.channels, int(np.prod(cfg.n_voxels)))
+        assert vol.is_contiguous() == cf
+        outs[cf] = (vol, cnt)
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    count = torch.from_numpy(gold["count"]).reshape(-1)
+    assert np.array_equal(outs[False][1].cpu().numpy(), count.numpy().astype(np.int32))
+    want = torch.from_numpy(gold["volume_mean"]).reshape(cfg.channels, -1) * (count.float() + 1e-8)
+    _close(outs[False][0], want, "BP_SUM channels-last")
