@@ -370,11 +370,13 @@ class ShardedScenePipeline:
         # higher priority: the combine's barrier / reduce CTAs are dispatched as soon as SM slots free up,
         # ahead of the next scene's queued sweep CTAs (at equal priority they wait for the sweep's last wave)
         self.s_comm = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_aux = torch.cuda.Stream(device=dev, priority=-1)      # small backward kernels under the sweep
         self._ev_part = [None, None]      # partials of slot written (compute stream)
         self._ev_free = [None, None]      # slot's partial buffer consumed by the combine (comm stream)
         self._graphs = [None, None]
         self.lg: Optional[LocalGeometry] = None
         self._g_feat = None
+        self._bwd_graphs: Dict = {}
         self._slot = 0
 
     # ------------------------------------------------------------------ setup
@@ -405,6 +407,7 @@ class ShardedScenePipeline:
         self.vl, self.vb = vl, vb
         self._graphs = [None, None]
         self._g_feat = None
+        self._bwd_graphs = {}
         torch.cuda.synchronize(dev)
 
     def _code(self, dtype):
@@ -514,7 +517,7 @@ class ShardedScenePipeline:
         return res
 
     # ------------------------------------------------------------------ backward
-    def backward(self, g_volume_mean: torch.Tensor, g_variance: torch.Tensor):
+    def backward(self, g_volume_mean: torch.Tensor, g_variance: torch.Tensor, use_graph: bool = True):
         """After ``forward`` (same slot): ``g_volume_mean`` [C,nx,ny,nz] (replicated on every rank),
         ``g_variance`` logical [Vb,C,D,Hf,Wf] in channels_last_3d for this rank's reference views.
         -> (g_feature [Vb,C,Hf,Wf] fp32 for the rank's own block, g_cost_out [Vb,2,D,Hf,Wf])."""
@@ -540,28 +543,62 @@ class ShardedScenePipeline:
             self.g_cost_out = torch.empty((vb, 2, d, hf, wf), dtype=torch.float32, device=dev)
             self.g_feature = torch.empty((vb, c, hf, wf), dtype=torch.float32, device=dev)
         slot = self._last_slot
-        count = self.count_local[slot]
         g_vol = g_volume_mean.reshape(c, n).float().contiguous()
         gv = g_variance if g_variance.permute(0, 2, 3, 4, 1).is_contiguous() else \
             g_variance.contiguous(memory_format=torch.channels_last_3d)
-        vdt = self._code(gv.dtype)
-        self._g_feat.zero_()
-        self.g_pn.zero_()
-        sv, s_t, sy, sx = self.est_depth.stride()
-        lib.call("mvsd_backproject_bwd", g_vol.data_ptr(), CHANNELS_FIRST, self._lib.BP_MEAN, count.data_ptr(),
-                 self.feat_cl.data_ptr(), fdt, hf, wf, geo.points.data_ptr(), geo.projection.data_ptr(),
-                 self.est_depth.data_ptr(), self.est_dens.data_ptr(), sv, sy, sx, s_t, float(cfg.voxel_size[2]),
-                 self._g_feat.data_ptr(), self.g_pn.data_ptr(), vb, c, geo.height, geo.width, t, n, st)
-        lib.call("mvsd_prob_norm_bwd", self.est_dens.data_ptr(), self.g_pn.data_ptr(), self.g_est_dens.data_ptr(),
-                 sv, sy, sx, s_t, vb, geo.height, geo.width, t, st)
-        sc = self.cost_out.stride()
-        lib.call("mvsd_depth_topk_bwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2], sc[4], self.est_idx.data_ptr(),
-                 None, None, None, self.g_est_dens.data_ptr(), None, None, 0, None, None,
-                 self.g_cost_out.data_ptr(), float(cfg.near_far_range[0]), float(cfg.depth_interval), 0,
-                 vb, d, hf, wf, t, st)
-        lib.call("mvsd_plane_sweep_bwd", gv.data_ptr(), vdt, CHANNELS_LAST, self.feat_cl.data_ptr(), fdt,
-                 lg.neighbor_ids_local.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(),
-                 self._g_feat.data_ptr(), vb, c, d, hf, wf, k, 0, vl, st)
+
+        def enqueue_local():
+            """zero-fills + back-projection / prob-norm / top-k / sweep backward into the accumulator;
+            current stream; capturable (no allocation, no host sync)"""
+            cur = torch.cuda.current_stream()
+            count = self.count_local[slot]
+            vdt = self._code(gv.dtype)
+            self._g_feat.zero_()
+            self.g_pn.zero_()
+            # the three small kernels run on a higher-priority side stream under the sweep backward
+            # (all of them RED into the same accumulator: the order does not matter)
+            self.s_aux.wait_stream(cur)
+            with torch.cuda.stream(self.s_aux):
+                sa_ = self.s_aux.cuda_stream
+                sv, s_t, sy, sx = self.est_depth.stride()
+                lib.call("mvsd_backproject_bwd", g_vol.data_ptr(), CHANNELS_FIRST, self._lib.BP_MEAN, count.data_ptr(),
+                         self.feat_cl.data_ptr(), fdt, hf, wf, geo.points.data_ptr(), geo.projection.data_ptr(),
+                         self.est_depth.data_ptr(), self.est_dens.data_ptr(), sv, sy, sx, s_t,
+                         float(cfg.voxel_size[2]), self._g_feat.data_ptr(), self.g_pn.data_ptr(), vb, c,
+                         geo.height, geo.width, t, n, sa_)
+                lib.call("mvsd_prob_norm_bwd", self.est_dens.data_ptr(), self.g_pn.data_ptr(),
+                         self.g_est_dens.data_ptr(), sv, sy, sx, s_t, vb, geo.height, geo.width, t, sa_)
+                sc = self.cost_out.stride()
+                lib.call("mvsd_depth_topk_bwd", self.cost_out.data_ptr(), sc[0], sc[1], sc[2], sc[4],
+                         self.est_idx.data_ptr(), None, None, None, self.g_est_dens.data_ptr(), None, None, 0, None,
+                         None, self.g_cost_out.data_ptr(), float(cfg.near_far_range[0]), float(cfg.depth_interval),
+                         0, vb, d, hf, wf, t, sa_)
+            lib.call("mvsd_plane_sweep_bwd", gv.data_ptr(), vdt, CHANNELS_LAST, self.feat_cl.data_ptr(), fdt,
+                     lg.neighbor_ids_local.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(),
+                     self._g_feat.data_ptr(), vb, c, d, hf, wf, k, 0, vl, cur.cuda_stream)
+            cur.wait_stream(self.s_aux)
+
+        # the local chain is replayed as one CUDA graph while the caller keeps handing in the same
+        # gradient buffers (a training loop's pre-allocated ones); new pointers -> captured again
+        key = (slot, g_vol.data_ptr(), gv.data_ptr(), gv.dtype)
+        if use_graph and g_vol.data_ptr() == g_volume_mean.data_ptr():
+            ent = self._bwd_graphs.get(key)
+            if ent is None:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    enqueue_local()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    enqueue_local()
+                if len(self._bwd_graphs) >= 4:
+                    self._bwd_graphs.clear()
+                ent = self._bwd_graphs[key] = (g, g_vol, gv)          # keeps the captured buffers alive
+            ent[0].replay()
+        else:
+            enqueue_local()
         # owners pull the halo contributions of their peers
         self._h_g.barrier(channel=0)
         if self._n_pull:
@@ -575,4 +612,5 @@ class ShardedScenePipeline:
         """Drop the captured graphs and peer-mapped buffers before the process group goes away."""
         torch.cuda.synchronize(self.device)
         self._graphs = [None, None]
+        self._bwd_graphs = {}
         self._g_feat = None
