@@ -614,6 +614,13 @@ def run_own_arm(args, cfg, cfg_json):
                                             "self-inflicted layout cost, not algorithmic bytes",
                                     "mb": round((abytes["pack"] + abytes["unpack"]) / 1e6, 1),
                                     "ms": round(kernels["pack"]["ms"] + kernels["unpack"]["ms"], 5)}}
+    # both denominators (measured copy bandwidth and the nominal 8 TB/s), and the
+    # back-projection's data-dependent traffic (passing (view, voxel) pairs x C x bytes per feature)
+    roofline["frac_of_nominal_8tbs"] = round(achieved / 8000.0, 4)
+    roofline["path_frac_of_nominal_8tbs"] = round(SURVEY_PATH_MB * 1e6 / (ms_per_step * 1e-3) / 1e9 / 8000.0, 4)
+    pairs = int(p0.count.sum().item())
+    roofline["backproject_passing_pairs"] = pairs
+    roofline["backproject_pairs_feature_mb"] = round(pairs * cfg.channels * p0.feat_cl.element_size() / 1e6, 1)
     ncu_traffic = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(ncu_traffic):
         try:
@@ -783,6 +790,20 @@ def run_own_arm(args, cfg, cfg_json):
         dist.destroy_process_group()
 
 
+def run_sweep(args):
+    """BASELINE.json configs[4]: D in {12..64} x V in {10..100} x feature maps up to 480x640, achieved
+    algorithmic GB/s of the two sweep kernels against the measured HBM peak (1 GPU; view-chunked)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sweep_chart", os.path.join(ROOT, "tools", "sweep_chart.py"))
+    sc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sc)
+    rows = sc.sweep(quick=args.sweep == "quick", verbose=False)
+    print(json.dumps({"metric": "plane-sweep kernels, achieved algorithmic GB/s vs HBM roofline",
+                      "config": {"workload": "BASELINE.json configs[4]: depth-plane / view-count / resolution sweep",
+                                 "channels": 256, "dtype": "bf16 features, f32 variance"},
+                      "hbm_peak_gbs": sc.peak(), "n_gpus": 1, "data": "synthetic", "rows": rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -799,7 +820,13 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the fp32-feature and eager-GPU legs")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the view-sharded V=80 leg")
     ap.add_argument("--sharded-views", type=int, default=80)
+    ap.add_argument("--sweep", choices=["quick", "full"], default=None,
+                    help="BASELINE.json configs[4] instead of the step benchmark: depth-plane / view-count / "
+                         "resolution sweep of the plane-sweep kernels (tools/sweep_chart.py), one JSON line")
     args = ap.parse_args()
+    if args.sweep:
+        run_sweep(args)
+        return
     args.warmup = max(args.warmup, 3 if args.impl == "own" else 1)
 
     from mvsdet_b200.scene import SceneConfig

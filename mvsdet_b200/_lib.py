@@ -60,6 +60,8 @@ class MvsdError(RuntimeError):
 def load() -> C.CDLL:
     """dlopen the library and type every entry point (no compute happens)."""
     global _lib
+    if _lib is not None:
+        return _lib
     with _lock:
         if _lib is None:
             if not os.path.isfile(LIB_PATH):

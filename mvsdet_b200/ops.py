@@ -29,7 +29,15 @@ __all__ = ["pack_features", "plane_sweep_variance", "homo_warp", "depth_topk", "
 # --------------------------------------------------------------------------
 # helpers
 # --------------------------------------------------------------------------
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device.  torch.cuda.current_stream()
+    builds a Stream object through three layers of device-index helpers (16 us per call, ten calls
+    per scene: 15 % of the drop-in's host time); the raw getter inductor uses is one C call."""
+    if _raw_stream is not None:
+        return _raw_stream(torch._C._cuda_getDevice())
     return torch.cuda.current_stream().cuda_stream
 
 

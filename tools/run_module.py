@@ -52,3 +52,16 @@ if os.environ.get("MVSD_PROFILE"):
             step(None)
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25))
+
+# host-side hot spots of the drop-in: cProfile over 200 steps (cumulative, top entries)
+if os.environ.get("MVSD_CPROFILE"):
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(200):
+        step(None)
+    pr.disable()
+    torch.cuda.synchronize()
+    st = pstats.Stats(pr)
+    st.sort_stats("cumulative").print_stats(45)
+    st.sort_stats("tottime").print_stats(25)

@@ -89,17 +89,12 @@ def run_config(v, d, hf, wf, c, budget_gb, backward, dev):
     return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default="gpurun_out/sweep_chart.json")
-    ap.add_argument("--budget-gb", type=float, default=24.0)
-    ap.add_argument("--quick", action="store_true")
-    a = ap.parse_args()
+def sweep(quick=False, budget_gb=24.0, verbose=True):
     dev = torch.device("cuda")
     pk = peak()
     grid = []
-    if a.quick:
-        grid = [(10, 16, 60, 80), (4, 64, 120, 160)]
+    if quick:
+        grid = [(10, 16, 60, 80), (20, 12, 60, 80), (4, 64, 120, 160), (2, 16, 480, 640)]
     else:
         for hf, wf in ((60, 80), (120, 160)):
             for d in (12, 16, 32, 48, 64):
@@ -109,14 +104,25 @@ def main():
             grid.append((10, d, 480, 640))
     rows = []
     for v, d, hf, wf in grid:
-        r = run_config(v, d, hf, wf, 256, a.budget_gb, backward=(hf * wf <= 160 * 120), dev=dev)
+        r = run_config(v, d, hf, wf, 256, budget_gb, backward=(hf * wf <= 160 * 120), dev=dev)
         r["fwd_frac_of_hbm_peak"] = round(r["fwd_gbs"] / pk, 3)
         if "bwd_gbs" in r:
             r["bwd_frac_of_hbm_peak"] = round(r["bwd_gbs"] / pk, 3)
         rows.append(r)
-        print(json.dumps(r), flush=True)
+        if verbose:
+            print(json.dumps(r), flush=True)
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/sweep_chart.json")
+    ap.add_argument("--budget-gb", type=float, default=24.0)
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    rows = sweep(a.quick, a.budget_gb)
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
-    json.dump(dict(hbm_peak_gbs=pk, rows=rows), open(a.out, "w"), indent=1)
+    json.dump(dict(hbm_peak_gbs=peak(), rows=rows), open(a.out, "w"), indent=1)
 
 
 if __name__ == "__main__":
