@@ -305,6 +305,57 @@ def time_eager_gpu(cfg, scene, dev, reps=3):
     return out
 
 
+def time_group_correlation(pipe, cfg, peak, groups=8, reps=20):
+    """mvsd_plane_sweep_groupcorr_fwd / _bwd on the benchmark scene's packed features (G = 8 groups of
+    32 channels): CUDA-event means, an L2 flush between repetitions."""
+    from mvsdet_b200 import _lib
+    dev = pipe.feat_cl.device
+    geo = pipe.geo
+    v, d, k = cfg.n_views, cfg.num_depth, geo.k
+    hf, wf = cfg.feat_hw
+    c = cfg.channels
+    out = torch.empty((v, k, d, hf, wf, groups), dtype=torch.float32, device=dev)
+    g_out = torch.randn_like(out)
+    acc = torch.zeros((v, hf, wf, c), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    fdt = _lib.BF16 if pipe.feat_cl.dtype == torch.bfloat16 else _lib.F32
+
+    def fwd():
+        _lib.call("mvsd_plane_sweep_groupcorr_fwd", pipe.feat_cl.data_ptr(), fdt, geo.neighbor_ids.data_ptr(),
+                  geo.hom.data_ptr(), geo.depth_values.data_ptr(), out.data_ptr(), v, c, d, hf, wf, k, groups,
+                  0, v, st)
+
+    def bwd():
+        _lib.call("mvsd_plane_sweep_groupcorr_bwd", g_out.data_ptr(), pipe.feat_cl.data_ptr(), fdt,
+                  geo.neighbor_ids.data_ptr(), geo.hom.data_ptr(), geo.depth_values.data_ptr(), acc.data_ptr(),
+                  v, c, d, hf, wf, k, groups, 0, v, st)
+
+    res = {}
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        ms = []
+        for _ in range(reps + 3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        res[name] = statistics.mean(ms[3:])
+    feat_b = pipe.feat_cl.numel() * pipe.feat_cl.element_size()
+    fwd_b = feat_b + out.numel() * 4
+    bwd_b = feat_b + out.numel() * 4 + acc.numel() * 4
+    return {"what": f"optional operator (SURVEY 8f rank 4): group-wise correlation volumes [V,k,{groups},D,H,W] over the "
+                    "same homography sweep (lss_fpn.py:485-506 arithmetic, warp-shuffle group sums); not part of the step",
+            "groups": groups, "fwd_ms": round(res["fwd"], 5), "bwd_ms": round(res["bwd"], 5),
+            "fwd_algorithmic_mb": round(fwd_b / 1e6, 1), "bwd_algorithmic_mb": round(bwd_b / 1e6, 1),
+            "fwd_frac_of_hbm_peak": round(fwd_b / (res["fwd"] * 1e-3) / 1e9 / peak, 4),
+            "bwd_frac_of_hbm_peak": round(bwd_b / (res["bwd"] * 1e-3) / 1e9 / peak, 4),
+            "note": "the output is 16x smaller than the variance volume, so the kernels are bound by the gather "
+                    "(L1 / L2 tap traffic and, in the backward, the un-merged fp32 RED payload), not by HBM"}
+
+
 def run_sharded_leg(args, dev, rank, world, dist):
     """BASELINE.json configs[2]: ONE test-time scene (V = --sharded-views, forward only) with its
     reference views sharded over the ranks and the voxel partials combined over NVLink, against
@@ -720,6 +771,14 @@ def run_own_arm(args, cfg, cfg_json):
         del pipes16, graphs16
         torch.cuda.empty_cache()
 
+    # ---- optional operator: group-wise correlation volume over the same sweep
+    corr_line = None
+    if world == 1 and feat_dtype == torch.bfloat16 and not args.no_extras:
+        try:
+            corr_line = time_group_correlation(p0, cfg, peak)
+        except Exception as exc:                       # noqa: BLE001
+            corr_line = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+
     eager = None
     if world == 1 and not args.no_extras:
         try:
@@ -776,6 +835,8 @@ def run_own_arm(args, cfg, cfg_json):
             line["f32_features"] = f32_line
         if bf16_line is not None:
             line["bf16_handoff"] = bf16_line
+        if corr_line is not None:
+            line["group_correlation"] = corr_line
         if eager is not None:
             line["eager_gpu"] = eager
         if sharded_line is not None:

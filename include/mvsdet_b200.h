@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MVSD_ABI_VERSION 2
+#define MVSD_ABI_VERSION 3
 
 typedef enum {
   MVSD_OK = 0,
@@ -135,6 +135,28 @@ int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout,
                          const float* depth_values, float* g_feat,
                          int V, int C, int D, int H, int W, int k, int ref_begin,
                          int n_feat_views, void* stream);
+
+/* ---- f4: group-wise correlation cost volume over the same sweep ----------- *
+ * The optional cost volume of SURVEY.md 8(f) rank 4; in the reference it is the
+ * inline arithmetic of mvs_models/lss_fpn.py:485-506 (a branch no shipped config
+ * reaches), here with MVSDet's own warp (mvs_models/module.py:105-146):
+ *   out[v,j,d,y,x,g] = mean_{c in group g} feat[ref_begin+v,y,x,c] * warped_j[v,c,d,y,x]
+ * for neighbour j = 0..k-1 and num_groups contiguous channel groups of
+ * C / num_groups channels (4, 8, 16, 32, 64 or 128 per group).
+ *   out   [V,k,D,H,W,num_groups] fp32 (groups innermost); a sample with all four
+ *         taps outside the map gives 0.  feat, nbr_ids, hom, depth_values,
+ *         ref_begin, n_feat_views: as for mvsd_plane_sweep_fwd; k >= 1.
+ * Backward: g_out has out's layout; g_feat (nhwc fp32, extent of feat) is ADDED to. */
+int mvsd_plane_sweep_groupcorr_fwd(const void* feat, int feat_dtype,
+                                   const int32_t* nbr_ids, const float* hom,
+                                   const float* depth_values, float* out,
+                                   int V, int C, int D, int H, int W, int k, int num_groups,
+                                   int ref_begin, int n_feat_views, void* stream);
+int mvsd_plane_sweep_groupcorr_bwd(const float* g_out, const void* feat, int feat_dtype,
+                                   const int32_t* nbr_ids, const float* hom,
+                                   const float* depth_values, float* g_feat,
+                                   int V, int C, int D, int H, int W, int k, int num_groups,
+                                   int ref_begin, int n_feat_views, void* stream);
 
 /* ---- a3 alone: homo_warping (mvs_models/module.py:105-146) --------------- *
  *   src  nhwc [B,H,W,C]; hom [B,12]; out [B,D,H,W,C];

@@ -23,7 +23,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvsdet_b200.so")
 OBJDIR = os.path.join(HERE, "_obj")
 SOURCES = ("capi.cu", "pack.cu", "scene_setup.cu", "plane_sweep_fwd.cu", "plane_sweep_bwd.cu",
-           "plane_sweep_bwd_run.cu", "depth_topk.cu", "backproject.cu", "voxel_p2p.cu")
+           "plane_sweep_bwd_run.cu", "group_corr.cu", "depth_topk.cu", "backproject.cu", "voxel_p2p.cu")
 HEADERS = (os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "plane_sweep.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "mvsdet_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

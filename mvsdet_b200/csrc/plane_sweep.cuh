@@ -50,6 +50,10 @@ struct SweepParams {
   int n_feat;              // views held by feat: neighbour ids outside [0, n_feat) give no sample
   int depth_per_pixel;     // homo_warping's [B,D,H,W] depth_values branch (module.py:130-133)
   int tiles_x, tiles_y, slices;
+  // group-wise correlation backward through the run kernel (group_corr.cu): g_out is the gradient of the
+  // cost volumes [V,k,D,H,W,corr_groups]; a channel's group is channel >> corr_cg_shift
+  int corr_groups, corr_cg_shift;
+  float corr_inv_cg;
 };
 
 struct SweepCoord {

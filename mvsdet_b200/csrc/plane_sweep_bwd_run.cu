@@ -359,15 +359,37 @@ struct PixelRaw {
   RawTaps<TIn, G> t0, t1;
 };
 
-template <typename TIn, typename TG, int KMAX, int G, bool FULL>
+// MODE 0: variance backward, gp -> this pixel-plane's dL/dvariance vector.  MODE 1: group-wise
+// correlation backward (group_corr.cu), gp -> the pixel-plane's corr_groups gradients of neighbour 0
+// (neighbour 1 is corr_nstride floats further); the lane's 2 x G group values travel in raw.g[0] as
+// (nbr 0 group of g = 0, g = 1, nbr 1 group of g = 0, g = 1), already divided by the group width.
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MODE>
 __device__ __forceinline__ void issue_pixel_loads(PixelRaw<TIn, TG, G>& raw, const WarpSample* smp,
                                                   const TG* __restrict__ gp, const TIn* __restrict__ rp,
-                                                  const TIn* const (&nsrc)[KMAX], int c0, int C) {
+                                                  const TIn* const (&nsrc)[KMAX], int c0, int C,
+                                                  const SweepParams& p) {
+  if constexpr (MODE == 1) {
+    const size_t nstride = (size_t)p.D * p.H * p.W * p.corr_groups;
+    const float* gq = reinterpret_cast<const float*>(gp);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const bool on = group_on<FULL>(c0, g, C);
-    raw.g[g] = on ? Raw<TG>::ld_stream_na(gp + 128 * g) : Raw<TG>::zero();
-    raw.r[g] = on ? Raw<TIn>::ld(rp + 128 * g) : Raw<TIn>::zero();
+    for (int g = 0; g < G; ++g) {
+      const bool on = group_on<FULL>(c0, g, C);
+      raw.r[g] = on ? Raw<TIn>::ld(rp + 128 * g) : Raw<TIn>::zero();
+      if (on) {
+        const int grp = (c0 + 128 * g) >> p.corr_cg_shift;
+        v[g] = __ldg(gq + grp) * p.corr_inv_cg;
+        v[2 + g] = __ldg(gq + nstride + grp) * p.corr_inv_cg;
+      }
+    }
+    raw.g[0] = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const bool on = group_on<FULL>(c0, g, C);
+      raw.g[g] = on ? Raw<TG>::ld_stream_na(gp + 128 * g) : Raw<TG>::zero();
+      raw.r[g] = on ? Raw<TIn>::ld(rp + 128 * g) : Raw<TIn>::zero();
+    }
   }
   // only the four tap offsets are needed to issue the loads: the second 16 bytes of a sample
   WarpSample a;
@@ -558,33 +580,60 @@ __device__ __forceinline__ void blend_taps_w(const RawTaps<TIn, G>& r, float4 wq
 }
 
 // sa: shared address of this pixel's first sample (32 bytes per sample)
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, int NSTG, bool V0, bool V1>
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int NSTG, bool V0, bool V1, int MODE>
 __device__ __forceinline__ void pixel_q3(RunPending<KMAX, G>& pend, PixelRaw<TIn, TG, G>& raw, unsigned sa,
                                          unsigned flags0, unsigned flags1, bool has_next,
                                          const WarpSample* smp_next, const TG* __restrict__ gp_next,
                                          const TIn* __restrict__ rp_next, const TIn* const (&nsrc)[KMAX],
                                          float* const (&ndst)[KMAX], uint32_t taddr, u64 inv_n2,
-                                         u64 two_inv_n2, int c0, int C, HoLite<KMAX>& ho) {
+                                         u64 two_inv_n2, int c0, int C, HoLite<KMAX>& ho, const SweepParams& p) {
   constexpr unsigned kS1 = 32u * (KMAX - 1);
   P4 w0[G], w1[G], gw0[G], gw1[G], ref[G], gv[G];
   if (V0) blend_taps_w<TIn, G>(raw.t0, lds_f4(sa), w0);
   if (V1) blend_taps_w<TIn, G>(raw.t1, lds_f4(sa + kS1), w1);
+  if constexpr (MODE == 1) {
+    // group-wise correlation: d ref += gq_0 w_0 + gq_1 w_1 ; d w_j = gq_j ref (gq: the group's gradient / width)
+    u64 q0[G], q1[G];
+    {
+      const float qv[4] = {raw.g[0].x, raw.g[0].y, raw.g[0].z, raw.g[0].w};
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    ref[g] = p4from(raw.r[g]);
-    gv[g] = p4scale(p4from(raw.g[g]), two_inv_n2);
-  }
-  if (has_next) issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, smp_next, gp_next, rp_next, nsrc, c0, C);
+      for (int g = 0; g < G; ++g) {
+        ref[g] = p4from(raw.r[g]);
+        q0[g] = pk2(qv[g], qv[g]);
+        q1[g] = pk2(qv[2 + g], qv[2 + g]);
+      }
+    }
+    if (has_next) issue_pixel_loads<TIn, TG, KMAX, G, FULL, MODE>(raw, smp_next, gp_next, rp_next, nsrc, c0, C, p);
+    if (V0 || V1) {
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    P4 mu = ref[g];
-    if (V0) mu = p4add(mu, w0[g]);
-    if (V1) mu = p4add(mu, w1[g]);
-    mu = p4scale(mu, inv_n2);
-    const uint32_t ta = taddr + 4u * (uint32_t)g;
-    tmem_st4(ta, p4fma(gv[g], p4sub(ref[g], mu), tmem_ld4(ta)));
-    if (V0) gw0[g] = p4mul(gv[g], p4sub(w0[g], mu));
-    if (V1) gw1[g] = p4mul(gv[g], p4sub(w1[g], mu));
+      for (int g = 0; g < G; ++g) {
+        const uint32_t ta = taddr + 4u * (uint32_t)g;
+        P4 acc = tmem_ld4(ta);
+        if (V0) acc = p4fma(w0[g], q0[g], acc);
+        if (V1) acc = p4fma(w1[g], q1[g], acc);
+        tmem_st4(ta, acc);
+        if (V0) gw0[g] = p4scale(ref[g], q0[g]);
+        if (V1) gw1[g] = p4scale(ref[g], q1[g]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      ref[g] = p4from(raw.r[g]);
+      gv[g] = p4scale(p4from(raw.g[g]), two_inv_n2);
+    }
+    if (has_next) issue_pixel_loads<TIn, TG, KMAX, G, FULL, MODE>(raw, smp_next, gp_next, rp_next, nsrc, c0, C, p);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      P4 mu = ref[g];
+      if (V0) mu = p4add(mu, w0[g]);
+      if (V1) mu = p4add(mu, w1[g]);
+      mu = p4scale(mu, inv_n2);
+      const uint32_t ta = taddr + 4u * (uint32_t)g;
+      tmem_st4(ta, p4fma(gv[g], p4sub(ref[g], mu), tmem_ld4(ta)));
+      if (V0) gw0[g] = p4mul(gv[g], p4sub(w0[g], mu));
+      if (V1) gw1[g] = p4mul(gv[g], p4sub(w1[g], mu));
+    }
   }
   if (V0)
     scatter_hl<G, FULL, NSTG, 0, KMAX>(ndst[0], gw0, lds_f4(sa), lds_u4(sa + 16u), pend.id_top[0], pend.top[0],
@@ -596,8 +645,9 @@ __device__ __forceinline__ void pixel_q3(RunPending<KMAX, G>& pend, PixelRaw<TIn
 }
 
 // requires p.k == KMAX
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, int NSTG>
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, int MINB, int NSTG, int MODE = 0>
 __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const SweepParams p) {
+  static_assert(MODE == 0 || (KMAX == 2 && sizeof(TG) == 4), "correlation mode: two neighbours, fp32 gradients");
   constexpr int kCols = kRun * G * 4;
   constexpr unsigned kSlot = 2u * G * 512u;
   extern __shared__ __align__(16) unsigned char s_dyn[];          // [kRunRows - 1][KMAX][NSTG] slots
@@ -620,14 +670,18 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
     const TIn* feat = static_cast<const TIn*>(p.feat);
     const size_t ref_off = ((size_t)(c.v + p.ref_begin) * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
     const TIn* ref_row = feat + ref_off;
-    const size_t plane_stride = (size_t)HW * C;
-    const TG* g_d = static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
+    // MODE 1: the upstream gradient is [V,k,D,H,W,groups]; gpix / plane_stride are its pixel / plane strides
+    const int gpix = MODE == 1 ? p.corr_groups : C;
+    const size_t plane_stride = MODE == 1 ? (size_t)HW * p.corr_groups : (size_t)HW * C;
+    const TG* g_d = MODE == 1
+        ? static_cast<const TG*>(p.g_out) + ((size_t)c.v * KMAX * p.D * HW + (size_t)c.y * p.W + c.x0) * p.corr_groups
+        : static_cast<const TG*>(p.g_out) + ((size_t)c.v * p.D * HW + (size_t)c.y * p.W + c.x0) * C + c.c0;
     const bool one_chunk = p.slices == 1;
     const unsigned pf_bytes = (unsigned)((one_chunk ? (size_t)c.npix * C : (size_t)min(128 * G, C - (c.c0 - 4 * lane))) *
                                          sizeof(TG)) & ~15u;
     const TG* pf_base = g_d - 4 * lane;
-    const bool pf_ok = pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
-                       ((plane_stride * sizeof(TG)) & 15) == 0;
+    const bool pf_ok = MODE == 0 && pf_bytes >= 16 && (reinterpret_cast<uintptr_t>(pf_base) & 15) == 0 &&
+                       ((plane_stride * sizeof(TG)) & 15) == 0;       // the correlation gradient is small: no L2 prefetch
     auto prefetch_plane = [&](int d) {
       if (!pf_ok || d >= p.D) return;
       const TG* q = pf_base + (size_t)d * plane_stride;
@@ -675,7 +729,7 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
     if (ppf < p.D) fill_run_samples_ho(s_tab[warp][1], s_flg[warp][1], p, c, ppf, ppf, lane, has_up, has_dn);
     __syncwarp();
     // pipeline prologue: first pixel of the first plane
-    issue_pixel_loads<TIn, TG, KMAX, G, FULL>(raw, s_tab[warp][0], g_d, ref_row, nsrc, c.c0, C);
+    issue_pixel_loads<TIn, TG, KMAX, G, FULL, MODE>(raw, s_tab[warp][0], g_d, ref_row, nsrc, c.c0, C, p);
     int buf = 0;
     for (int d0 = 0; d0 < p.D; d0 += ppf, buf ^= 1) {
       const int dend = min(p.D, d0 + ppf);
@@ -707,17 +761,17 @@ __global__ void __launch_bounds__(kRunThreads, MINB) sweep_bwd_runs_kernel(const
           const bool in_run = i + 1 < c.npix;
           const bool has_next = in_run || more_planes;
           const WarpSample* smp_next = in_run ? tab + (i + 1) * KMAX : tab_next;
-          const TG* gp_next = in_run ? g_d + (i + 1) * C : g_d + plane_stride;
+          const TG* gp_next = in_run ? g_d + (i + 1) * gpix : g_d + plane_stride;
           const TIn* rp_next = in_run ? ref_row + (i + 1) * C : ref_row;
           const uint32_t ta = tbase + 4u * (uint32_t)(i * G);
           if (v0 && v1)
-            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, true, true>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, true, true, MODE>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho, p);
           else if (v0)
-            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, true, false>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, true, false, MODE>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho, p);
           else if (v1)
-            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, false, true>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, false, true, MODE>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho, p);
           else
-            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, false, false>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho);
+            pixel_q3<TIn, TG, KMAX, G, FULL, NSTG, false, false, MODE>(pend, raw, sa, f0, f1, has_next, smp_next, gp_next, rp_next, nsrc, ndst, ta, inv_n2, two_inv_n2, c.c0, C, ho, p);
         }
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
@@ -784,6 +838,37 @@ static int launch_bwd_run_t(SweepParams& p, cudaStream_t st) {
 #undef MVSD_RUN
   count_launch();
   return check_launch("plane_sweep_bwd(run)");
+}
+
+// Group-wise correlation backward (group_corr.cu) through the hand-off kernel: bf16 features, k = 2.
+// Returns -1 when this configuration is not built (the caller falls back to its pixel kernel).
+int launch_bwd_run_corr(SweepParams& p, int feat_dtype, cudaStream_t st) {
+  if (feat_dtype != MVSD_BF16 || p.k != 2) return -1;
+  typedef __nv_bfloat16 TIn;
+  const int G = sweep_groups(p.C);
+  p.tiles_x = (p.W + kRun - 1) / kRun;
+  p.tiles_y = (p.H + kRunRows - 1) / kRunRows;
+  p.slices = (p.C + 128 * G - 1) / (128 * G);
+  const long long blocks = (long long)p.V * p.slices * p.tiles_y * p.tiles_x;
+  if (blocks > 2147483647LL) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_groupcorr_bwd: grid too large");
+  dim3 grid((unsigned)blocks);
+  const bool full = p.C % (128 * G) == 0;
+#define MVSD_RUNC(GG, FU)                                                                   \
+  do {                                                                                      \
+    auto kern = sweep_bwd_runs_kernel<TIn, float, 2, GG, FU, kRunQMinBlocks, 2, 1>;         \
+    constexpr size_t dyn = run_slot_bytes<2, GG, 2>();                                      \
+    static bool attr_set = false;                                                           \
+    if (!attr_set) {                                                                        \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);    \
+      attr_set = true;                                                                      \
+    }                                                                                       \
+    kern<<<grid, kRunThreads, dyn, st>>>(p);                                                \
+  } while (0)
+  if (G == 2) { if (full) MVSD_RUNC(2, true); else MVSD_RUNC(2, false); }
+  else { if (full) MVSD_RUNC(1, true); else MVSD_RUNC(1, false); }
+#undef MVSD_RUNC
+  count_launch();
+  return check_launch("plane_sweep_groupcorr_bwd(run)");
 }
 
 int launch_bwd_run(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st) {

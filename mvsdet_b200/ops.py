@@ -317,6 +317,70 @@ def plane_sweep_variance(feat: torch.Tensor, nbr_ids: torch.Tensor, hom: torch.T
                                      out_dtype, int(ref_begin), grad_sink)
 
 
+class _GroupCorrelation(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, nbr_ids, hom, depth_values, num_groups, ref_begin, sink=None):
+        vf, c, h, w = feat.shape
+        v, k = nbr_ids.shape
+        d = depth_values.shape[1]
+        out = torch.empty((v, k, d, h, w, num_groups), dtype=torch.float32, device=feat.device)
+        _lib.call("mvsd_plane_sweep_groupcorr_fwd", feat.data_ptr(), _code(feat.dtype), nbr_ids.data_ptr(),
+                  hom.data_ptr(), depth_values.data_ptr(), out.data_ptr(), v, c, d, h, w, k, num_groups,
+                  ref_begin, vf, _stream())
+        ctx.save_for_backward(feat, nbr_ids, hom, depth_values)
+        ctx.meta = (num_groups, ref_begin)
+        ctx.sink = sink
+        return out.permute(0, 1, 5, 2, 3, 4)              # logical [V,k,G,D,H,W], groups innermost in memory
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, nbr_ids, hom, depth_values = ctx.saved_tensors
+        num_groups, ref_begin = ctx.meta
+        vf, c, h, w = feat.shape
+        v, k = nbr_ids.shape
+        d = depth_values.shape[1]
+        g = g.float().permute(0, 1, 3, 4, 5, 2).contiguous()          # no copy when it arrives in out's layout
+        acc = ctx.sink.get() if ctx.sink is not None else None
+        g_feat = acc if acc is not None else _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
+        _lib.call("mvsd_plane_sweep_groupcorr_bwd", g.data_ptr(), feat.data_ptr(), _code(feat.dtype),
+                  nbr_ids.data_ptr(), hom.data_ptr(), depth_values.data_ptr(), g_feat.data_ptr(),
+                  v, c, d, h, w, k, num_groups, ref_begin, vf, _stream())
+        if acc is not None:
+            return None, None, None, None, None, None, None
+        return (g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)), None, None, None, None, None, None
+
+
+def plane_sweep_group_correlation(feat: torch.Tensor, nbr_ids: torch.Tensor, hom: torch.Tensor,
+                                  depth_values: torch.Tensor, num_groups: int = 8, ref_begin: int = 0,
+                                  grad_sink: Optional[FeatureGradSink] = None) -> torch.Tensor:
+    """Group-wise correlation cost volumes over the plane sweep (the reference's
+    arithmetic is mvs_models/lss_fpn.py:485-506, the warp mvs_models/module.py:105-146): same arguments
+    as ``plane_sweep_variance``; -> logical [V,k,num_groups,D,H,W] fp32, one volume per neighbour,
+    ``mean over the group's channels of ref * warped_j``.  C / num_groups must be 4 ... 128 and divide
+    128.  The memory order is [V,k,D,H,W,num_groups]."""
+    for n, t in (("feat", feat), ("nbr_ids", nbr_ids), ("hom", hom), ("depth_values", depth_values)):
+        _need_cuda(n, t)
+    if not _is_nhwc(feat):
+        raise ValueError("feat must be channels_last; use ops.pack_features")
+    if nbr_ids.dtype != torch.int32 or not nbr_ids.is_contiguous():
+        raise ValueError("nbr_ids must be contiguous int32 [V,k]")
+    v, k = nbr_ids.shape
+    if k < 1:
+        raise ValueError("group correlation needs at least one neighbour")
+    if tuple(hom.shape) != (v, k, 12) or depth_values.shape[0] != v or depth_values.dim() != 2:
+        raise ValueError("nbr_ids [V,k], hom [V,k,12] and depth_values [V,D] must agree")
+    if ref_begin < 0 or ref_begin + v > feat.shape[0]:
+        raise ValueError("reference views [ref_begin, ref_begin+V) exceed feat")
+    if hom.dtype != torch.float32 or depth_values.dtype != torch.float32:
+        raise ValueError("hom and depth_values must be float32")
+    if num_groups < 1 or feat.shape[1] % num_groups != 0:
+        raise ValueError("the channel count must be divisible by num_groups")
+    if grad_sink is not None and grad_sink.shape != tuple(feat.shape):
+        raise ValueError("grad_sink belongs to a different feature tensor")
+    return _GroupCorrelation.apply(feat, nbr_ids, hom.contiguous(), depth_values.contiguous(),
+                                   int(num_groups), int(ref_begin), grad_sink)
+
+
 class _HomoWarp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, hom, depth_values, out_dtype):

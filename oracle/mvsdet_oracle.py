@@ -39,7 +39,7 @@ import torch.nn.functional as F
 
 __all__ = [
     "knn", "get_nearest_pose_ids", "collect_proj", "homography",
-    "homo_warping", "warp_closed_form", "plane_sweep_variance",
+    "homo_warping", "warp_closed_form", "plane_sweep_variance", "group_correlation", "scene_group_correlation",
     "depth_values_for", "depth_probability", "sample_depth_prob",
     "compute_avg_depth", "compute_projection", "feature_intrinsics",
     "get_points", "backproject_weigh", "aggregate_views", "hot_path",
@@ -237,6 +237,45 @@ def plane_sweep_variance(feature, w2c, feat_intrinsic, neighbor_ids, depth_value
     if training:
         return volume_sq_sum / (k + 1) - (volume_sum / (k + 1)) ** 2
     return volume_sq_sum.div_(k + 1).sub_(volume_sum.div_(k + 1).pow_(2))
+
+
+def group_correlation(feature, w2c, feat_intrinsic, neighbor_ids, depth_values, num_groups: int):
+    """[V,C,Hf,Wf] -> group-wise correlation cost volumes [V,k,G,D,Hf,Wf], one per neighbour
+    (SURVEY.md 8f rank 4).  The arithmetic follows mvs_models/lss_fpn.py:485-506 statement by
+    statement -- reshape the warped and the reference features into ``num_groups`` contiguous channel
+    groups, ``torch.mean(ref.unsqueeze(3) * warped, axis=2)`` -- with MVSDet's own warp
+    (``homo_warping``, module.py:105-146) and neighbour selection in place of that file's
+    BEVStereo-specific ones.  The reference then feeds every volume to a small 3-D net and averages the
+    scores over the neighbours (:506-508); that net is outside the path, the volumes are the hand-off."""
+    v, c, hf, wf = feature.shape
+    k = neighbor_ids.shape[1]
+    d = depth_values.shape[-1]
+    all_proj = torch.matmul(feat_intrinsic if feat_intrinsic.dim() == 3
+                            else feat_intrinsic.unsqueeze(0).repeat(w2c.shape[0], 1, 1), w2c)
+    ref_proj = all_proj[:v]
+    nei_projs = torch.unbind(all_proj[neighbor_ids.reshape(-1)].view(v, k, 4, 4), dim=1)
+    if depth_values.dim() == 1:
+        depth_values = depth_values.unsqueeze(0).repeat(v, 1)
+    ref_feat = feature.reshape(v, num_groups, c // num_groups, hf, wf)                      # :499-501
+    costs = []
+    for j in range(k):
+        warped = homo_warping(feature[neighbor_ids[:, j]], nei_projs[j], ref_proj, depth_values)
+        warped = warped.reshape(v, num_groups, c // num_groups, d, hf, wf)                  # :496-498
+        costs.append(torch.mean(ref_feat.unsqueeze(3) * warped, axis=2))                    # :502-503
+    return torch.stack(costs, dim=1)
+
+
+def scene_group_correlation(feature, img_meta, *, near_far_range, num_depth, num_groups, stride: int = 4):
+    """``group_correlation`` with the scene glue of ``hot_path`` (feature-level intrinsics, pose
+    neighbours, depth planes: mvsdet.py:422-434, :222-225)."""
+    v = feature.shape[0]
+    ratio = img_meta["ori_shape"][0] / (img_meta["img_shape"][0] / stride)
+    w2c = torch.as_tensor(np.array(img_meta["lidar2img"]["extrinsic"]))
+    intr = torch.as_tensor(np.array(img_meta["lidar2img"]["intrinsic"]))
+    k_feat = feature_intrinsics(intr, ratio)
+    neighbor_ids = get_nearest_pose_ids(w2c.inverse(), min(2, v - 1))
+    dvals = torch.as_tensor(depth_values_for(near_far_range, num_depth))
+    return group_correlation(feature, w2c, k_feat, neighbor_ids, dvals, num_groups)
 
 
 # --------------------------------------------------------------------------

@@ -125,3 +125,43 @@ def make_self(near_far_range, num_depth):
                                   self.depth_interval, dtype=np.float32)
     assert len(self.depth_values) == num_depth
     return self
+
+
+def group_correlation_statements():
+    """The reference's group-wise correlation arithmetic, executed verbatim: the three assignments
+    of ``LSSFPN._generate_cost_volume`` (mvs_models/lss_fpn.py:496-503) that reshape the warped and the
+    reference features into channel groups and take ``torch.mean(ref.unsqueeze(3) * warped, axis=2)``.
+    ``lss_fpn.py`` cannot be imported (mmdet), so the statements are sliced out with ``ast``.
+
+    -> f(ref_feat [B,C,H,W], warped [B,C,D,H,W], num_groups) -> feat_cost [B,G,D,H,W]"""
+    import torch
+    path = os.path.join(_NERFDET, "mvs_models", "lss_fpn.py")
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    fn = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "_generate_cost_volume":
+            fn = node
+    if fn is None:
+        raise RuntimeError("lss_fpn.py: _generate_cost_volume not found")
+    wanted = []
+    for node in ast.walk(fn):
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name):
+            name = node.targets[0].id
+            src = ast.unparse(node.value)
+            if (name == "warped_stereo_fea" and ".reshape(" in src and "homo_warping" not in src) \
+                    or name in ("ref_stereo_feat", "feat_cost"):
+                wanted.append(node)
+    wanted.sort(key=lambda n: n.lineno)
+    if [n.targets[0].id for n in wanted] != ["warped_stereo_fea", "ref_stereo_feat", "feat_cost"]:
+        raise RuntimeError("lss_fpn.py: unexpected shape of the group-correlation statements")
+    code = compile(ast.Module(body=wanted, type_ignores=[]), path, "exec")
+
+    def run(ref_feat, warped, num_groups):
+        b, c, h, w = ref_feat.shape
+        ns = {"torch": torch, "self": types.SimpleNamespace(num_groups=num_groups, num_samples=warped.shape[2]),
+              "batch_size": b, "num_channels": c, "height": h, "width": w,
+              "stereo_feats_all_sweeps": [ref_feat], "sweep_index": 0, "warped_stereo_fea": warped}
+        exec(code, ns)  # noqa: S102 - reference code
+        return ns["feat_cost"]
+    return run

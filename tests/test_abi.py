@@ -63,7 +63,7 @@ def test_prototype_arity_matches_ctypes_table():
 def test_load_info_and_status_strings():
     _lib = _build_if_needed()
     lib = _lib.load()
-    assert lib.mvsd_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.mvsd_abi_version() == _lib.ABI_VERSION == 3
     assert b"sm_100a" in lib.mvsd_build_info()
     assert lib.mvsd_status_string(0) == b"ok"
     assert lib.mvsd_status_string(1) == b"invalid argument"
@@ -93,6 +93,10 @@ def test_invalid_arguments_fail_before_any_launch():
     assert st == _lib.ERR_UNSUPPORTED                    # k must be <= V-1
     st = lib.mvsd_scene_setup(one, one, 0, one, one, one, one, one, 4, 2, 3, 2, None)
     assert st == _lib.ERR_INVALID_ARG                    # reference views [3,5) of 4
+    st = lib.mvsd_plane_sweep_groupcorr_fwd(one, 0, one, one, one, one, 2, 24, 4, 4, 4, 1, 2, 0, 2, None)
+    assert st == _lib.ERR_UNSUPPORTED and b"per group" in lib.mvsd_last_error()    # 12 channels per group
+    st = lib.mvsd_plane_sweep_groupcorr_bwd(one, one, 0, one, one, one, one, 2, 24, 4, 4, 4, 1, 5, 0, 2, None)
+    assert st == _lib.ERR_INVALID_ARG                    # 24 channels, 5 groups
     st = lib.mvsd_backproject_fwd(None, 0, 4, 4, None, None, None, None, 0, 0, 0, 0, 0.2, 7, None,
                                   0, None, None, None, 1, 8, 4, 4, 3, 10, None)
     assert st == _lib.ERR_INVALID_ARG                    # bad mode

@@ -111,3 +111,29 @@ def test_costreg_restatement_equals_reference_class():
         theirs.train(train)
         mine.train(train)
         assert torch.equal(theirs(x.clone()), mine(x.clone()))
+
+
+def test_group_correlation_equals_reference_statements(ref):
+    """the oracle's group-wise correlation against the reference's own statements
+    (mvs_models/lss_fpn.py:496-503, sliced and executed verbatim) fed with the reference's own
+    homo_warping of the same neighbours."""
+    from oracle import mvsdet_oracle as O
+    cfg = tiny_config(n_views=5, channels=32, num_depth=6)
+    scene = make_scene(cfg, 211)
+    feature = scene["feature"]
+    groups = 8
+    got = O.scene_group_correlation(feature, scene["img_meta"], near_far_range=cfg.near_far_range,
+                                    num_depth=cfg.num_depth, num_groups=groups, stride=cfg.stride)
+    stmts = ref_loader.group_correlation_statements()
+    v = feature.shape[0]
+    ratio = scene["img_meta"]["ori_shape"][0] / (scene["img_meta"]["img_shape"][0] / cfg.stride)
+    w2c = torch.as_tensor(np.array(scene["img_meta"]["lidar2img"]["extrinsic"]))
+    k_feat = O.feature_intrinsics(torch.as_tensor(np.array(scene["img_meta"]["lidar2img"]["intrinsic"])), ratio)
+    nbr = ref.get_nearest_pose_ids(w2c.inverse(), w2c.inverse(), 2, maskself=True)       # mvsdet.py:434
+    proj = torch.matmul(k_feat.unsqueeze(0).repeat(v, 1, 1), w2c)
+    dvals = torch.as_tensor(O.depth_values_for(cfg.near_far_range, cfg.num_depth)).unsqueeze(0).repeat(v, 1)
+    assert tuple(got.shape) == (v, 2, groups, cfg.num_depth, *cfg.feat_hw)
+    for j in range(2):
+        warped = ref.homo_warping(feature[nbr[:, j]], proj[nbr[:, j]], proj, dvals)
+        want = stmts(feature, warped, groups)
+        assert_close(got[:, j], want, rtol=1e-6, atol=1e-6, what=f"group correlation, neighbour {j}")
