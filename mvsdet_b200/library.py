@@ -18,6 +18,8 @@ Operators (reference lines as in ``ops.py``):
 
   plane_sweep_variance(feat, nbr_ids, hom, depth_values, out_bf16=False, ref_begin=0) -> variance
       mvsdet.py:439-467 + mvs_models/module.py:105-146
+  plane_sweep_group_correlation(feat, nbr_ids, hom, depth_values, num_groups=8, ref_begin=0) -> [V,k,G,D,H,W]
+      mvs_models/lss_fpn.py:485-506 over mvs_models/module.py:105-146 (optional operator)
   depth_topk(cost_out, near, interval, topk, raw=False)
       -> (prob_volume, off_pred, est_depth, est_densities, est_idx, depth_coding)
       mvsdet.py:470-482, :266-283, :298-317
@@ -36,7 +38,8 @@ from torch import Tensor
 from . import ops as _ops
 from ._lib import BP_MEAN, BP_SUM
 
-__all__ = ["plane_sweep_variance", "depth_topk", "backproject_aggregate", "voxel_normalize"]
+__all__ = ["plane_sweep_variance", "plane_sweep_group_correlation", "depth_topk", "backproject_aggregate",
+           "voxel_normalize"]
 
 _NS = "mvsdet_b200"
 
@@ -104,6 +107,62 @@ def _sweep_backward(ctx, g):
 
 
 plane_sweep_variance.register_autograd(_sweep_backward, setup_context=_sweep_setup)
+
+
+# --------------------------------------------------------------------------
+# group-wise correlation volume (optional operator)
+# --------------------------------------------------------------------------
+@torch.library.custom_op(f"{_NS}::plane_sweep_group_correlation", mutates_args=(), device_types="cuda")
+def plane_sweep_group_correlation(feat: Tensor, nbr_ids: Tensor, hom: Tensor, depth_values: Tensor,
+                                  num_groups: int = 8, ref_begin: int = 0) -> Tensor:
+    _check(_ops._is_nhwc(feat), "feat must be channels_last; use ops.pack_features")
+    _check(nbr_ids.dtype == torch.int32 and nbr_ids.is_contiguous(), "nbr_ids must be contiguous int32 [V,k]")
+    v, k = nbr_ids.shape
+    _check(k >= 1, "group correlation needs at least one neighbour")
+    _check(tuple(hom.shape) == (v, k, 12) and depth_values.dim() == 2 and depth_values.shape[0] == v,
+           "nbr_ids [V,k], hom [V,k,12] and depth_values [V,D] must agree")
+    _check(0 <= ref_begin and ref_begin + v <= feat.shape[0], "reference views [ref_begin, ref_begin+V) exceed feat")
+    _check(hom.dtype == torch.float32 and depth_values.dtype == torch.float32, "hom and depth_values must be float32")
+    _check(num_groups >= 1 and feat.shape[1] % num_groups == 0, "the channel count must be divisible by num_groups")
+    return _ops._corr_fwd_raw(feat, nbr_ids, hom.contiguous(), depth_values.contiguous(), int(num_groups),
+                              int(ref_begin))
+
+
+@plane_sweep_group_correlation.register_fake
+def _(feat, nbr_ids, hom, depth_values, num_groups=8, ref_begin=0):
+    _, _, h, w = feat.shape
+    v, k = nbr_ids.shape
+    return torch.empty((v, k, depth_values.shape[1], h, w, num_groups), dtype=torch.float32,
+                       device=feat.device).permute(0, 1, 5, 2, 3, 4)
+
+
+@torch.library.custom_op(f"{_NS}::plane_sweep_group_correlation_bwd", mutates_args=(), device_types="cuda")
+def plane_sweep_group_correlation_bwd(g: Tensor, feat: Tensor, nbr_ids: Tensor, hom: Tensor,
+                                      depth_values: Tensor, num_groups: int, ref_begin: int) -> Tensor:
+    return _ops._corr_bwd_raw(g, feat, nbr_ids, hom, depth_values, int(num_groups), int(ref_begin))
+
+
+@plane_sweep_group_correlation_bwd.register_fake
+def _(g, feat, nbr_ids, hom, depth_values, num_groups, ref_begin):
+    v, c, h, w = feat.shape
+    return _nhwc_like(v, c, h, w, feat.dtype, feat.device)
+
+
+def _corr_setup(ctx, inputs, output):
+    feat, nbr_ids, hom, depth_values, num_groups, ref_begin = inputs
+    ctx.save_for_backward(feat, nbr_ids, hom, depth_values)
+    ctx.meta = (num_groups, ref_begin)
+
+
+def _corr_backward(ctx, g):
+    feat, nbr_ids, hom, depth_values = ctx.saved_tensors
+    num_groups, ref_begin = ctx.meta
+    g_feat = plane_sweep_group_correlation_bwd(g, feat, nbr_ids, hom.contiguous(), depth_values.contiguous(),
+                                               num_groups, ref_begin)
+    return g_feat, None, None, None, None, None
+
+
+plane_sweep_group_correlation.register_autograd(_corr_backward, setup_context=_corr_setup)
 
 
 # --------------------------------------------------------------------------

@@ -317,37 +317,50 @@ def plane_sweep_variance(feat: torch.Tensor, nbr_ids: torch.Tensor, hom: torch.T
                                      out_dtype, int(ref_begin), grad_sink)
 
 
+def _corr_fwd_raw(feat, nbr_ids, hom, depth_values, num_groups, ref_begin):
+    """enqueue mvsd_plane_sweep_groupcorr_fwd; -> logical [V,k,G,D,H,W] fp32, groups innermost in memory"""
+    vf, c, h, w = feat.shape
+    v, k = nbr_ids.shape
+    d = depth_values.shape[1]
+    out = torch.empty((v, k, d, h, w, num_groups), dtype=torch.float32, device=feat.device)
+    _lib.call("mvsd_plane_sweep_groupcorr_fwd", feat.data_ptr(), _code(feat.dtype), nbr_ids.data_ptr(),
+              hom.data_ptr(), depth_values.data_ptr(), out.data_ptr(), v, c, d, h, w, k, num_groups,
+              ref_begin, vf, _stream())
+    return out.permute(0, 1, 5, 2, 3, 4)
+
+
+def _corr_bwd_raw(g, feat, nbr_ids, hom, depth_values, num_groups, ref_begin, acc=None):
+    """enqueue mvsd_plane_sweep_groupcorr_bwd; -> dL/dfeat in feat's dtype (channels_last), or None
+    when it was accumulated into the fp32 accumulator ``acc`` (FeatureGradSink)"""
+    vf, c, h, w = feat.shape
+    v, k = nbr_ids.shape
+    d = depth_values.shape[1]
+    g = g.float().permute(0, 1, 3, 4, 5, 2).contiguous()          # no copy when it arrives in out's layout
+    g_feat = acc if acc is not None else _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
+    _lib.call("mvsd_plane_sweep_groupcorr_bwd", g.data_ptr(), feat.data_ptr(), _code(feat.dtype),
+              nbr_ids.data_ptr(), hom.data_ptr(), depth_values.data_ptr(), g_feat.data_ptr(),
+              v, c, d, h, w, k, num_groups, ref_begin, vf, _stream())
+    if acc is not None:
+        return None
+    return g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)
+
+
 class _GroupCorrelation(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, nbr_ids, hom, depth_values, num_groups, ref_begin, sink=None):
-        vf, c, h, w = feat.shape
-        v, k = nbr_ids.shape
-        d = depth_values.shape[1]
-        out = torch.empty((v, k, d, h, w, num_groups), dtype=torch.float32, device=feat.device)
-        _lib.call("mvsd_plane_sweep_groupcorr_fwd", feat.data_ptr(), _code(feat.dtype), nbr_ids.data_ptr(),
-                  hom.data_ptr(), depth_values.data_ptr(), out.data_ptr(), v, c, d, h, w, k, num_groups,
-                  ref_begin, vf, _stream())
+        out = _corr_fwd_raw(feat, nbr_ids, hom, depth_values, num_groups, ref_begin)
         ctx.save_for_backward(feat, nbr_ids, hom, depth_values)
         ctx.meta = (num_groups, ref_begin)
         ctx.sink = sink
-        return out.permute(0, 1, 5, 2, 3, 4)              # logical [V,k,G,D,H,W], groups innermost in memory
+        return out
 
     @staticmethod
     def backward(ctx, g):
         feat, nbr_ids, hom, depth_values = ctx.saved_tensors
         num_groups, ref_begin = ctx.meta
-        vf, c, h, w = feat.shape
-        v, k = nbr_ids.shape
-        d = depth_values.shape[1]
-        g = g.float().permute(0, 1, 3, 4, 5, 2).contiguous()          # no copy when it arrives in out's layout
         acc = ctx.sink.get() if ctx.sink is not None else None
-        g_feat = acc if acc is not None else _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
-        _lib.call("mvsd_plane_sweep_groupcorr_bwd", g.data_ptr(), feat.data_ptr(), _code(feat.dtype),
-                  nbr_ids.data_ptr(), hom.data_ptr(), depth_values.data_ptr(), g_feat.data_ptr(),
-                  v, c, d, h, w, k, num_groups, ref_begin, vf, _stream())
-        if acc is not None:
-            return None, None, None, None, None, None, None
-        return (g_feat if feat.dtype == torch.float32 else g_feat.to(feat.dtype)), None, None, None, None, None, None
+        g_feat = _corr_bwd_raw(g, feat, nbr_ids, hom, depth_values, num_groups, ref_begin, acc)
+        return g_feat, None, None, None, None, None, None
 
 
 def plane_sweep_group_correlation(feat: torch.Tensor, nbr_ids: torch.Tensor, hom: torch.Tensor,

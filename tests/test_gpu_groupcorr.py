@@ -95,3 +95,27 @@ def test_group_correlation_rejects_bad_group_width():
         ops.plane_sweep_group_correlation(feat, nbr, hom, dv, num_groups=2)
     with pytest.raises(ValueError):                      # not divisible at all
         ops.plane_sweep_group_correlation(feat, nbr, hom, dv, num_groups=5)
+
+
+def test_group_correlation_dispatcher_op_matches_autograd_function():
+    """torch.ops.mvsdet_b200.plane_sweep_group_correlation (library.py) == ops.plane_sweep_group_correlation,
+    values and gradient, plus torch.library.opcheck of the registration"""
+    from mvsdet_b200 import library as L, ops
+    from mvsdet_b200.hotpath import MVSDetHotPath
+    cfg = tiny_config(n_views=4, channels=64, num_depth=5)
+    dev = torch.device("cuda")
+    scene = make_scene(cfg, 9, with_grads=False)
+    mod = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk, stride=cfg.stride)
+    geo = mod.geometry(scene["img_meta"], dev)
+    base = scene["feature"].to(dev).contiguous(memory_format=torch.channels_last)
+    fa, fb = base.clone().requires_grad_(True), base.clone().requires_grad_(True)
+    a = ops.plane_sweep_group_correlation(fa, geo.neighbor_ids, geo.hom, geo.depth_values, 8)
+    b = L.plane_sweep_group_correlation(fb, geo.neighbor_ids, geo.hom, geo.depth_values, 8)
+    assert torch.equal(a, b)
+    g = torch.randn_like(a)
+    ga, = torch.autograd.grad(a, fa, g)
+    gb, = torch.autograd.grad(b, fb, g)
+    _close(gb, ga, "dispatcher op gradient", rtol=1e-5, atol_scale=1e-5)      # fp32 RED order differs
+    torch.library.opcheck(torch.ops.mvsdet_b200.plane_sweep_group_correlation.default,
+                          (base, geo.neighbor_ids, geo.hom, geo.depth_values, 8, 0),
+                          test_utils=("test_schema", "test_faketensor"))

@@ -46,6 +46,18 @@ def test_plane_sweep_fake_layout(out_bf16):
     assert tuple(g.shape) == (V, C, H, W) and g.permute(0, 2, 3, 1).is_contiguous()
 
 
+def test_group_correlation_fake_layout():
+    """optional operator: logical [V,k,G,D,H,W], groups innermost in memory"""
+    s = _meta_scene()
+    cost = L.plane_sweep_group_correlation(s["feat"], s["nbr"], s["hom"], s["dv"], 4)
+    assert tuple(cost.shape) == (V, K, 4, D, H, W) and cost.dtype == torch.float32
+    assert cost.permute(0, 1, 3, 4, 5, 2).is_contiguous()
+    g, = torch.autograd.grad(cost, s["feat"], torch.empty_like(cost))
+    assert tuple(g.shape) == (V, C, H, W) and g.permute(0, 2, 3, 1).is_contiguous()
+    schema = str(torch.ops.mvsdet_b200.plane_sweep_group_correlation.default._schema)
+    assert schema.startswith("mvsdet_b200::plane_sweep_group_correlation(") and "num_groups=8" in schema
+
+
 def test_view_slice_fake_layout():
     """view-sharded form: V_local reference views out of Vf packed views"""
     s = _meta_scene()
