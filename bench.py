@@ -723,6 +723,31 @@ def run_own_arm(args, cfg, cfg_json):
                       "what": "MVSDetHotPath forward + torch.autograd backward, scene geometry rebuilt every "
                               "call (two host ATen calls + one setup kernel), shared fp32 gradient accumulator, "
                               "caching allocator, no CUDA graph"}
+        if not args.no_extras:
+            # the opt-in bit-reproducible backward (64-bit fixed-point integer REDs, un-merged scatter)
+            hot_det = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
+                                    stride=cfg.stride, feature_dtype=feat_dtype, deterministic=True)
+
+            def det_step():
+                res = hot_det(m_feat, host_scene["img_meta"], cost_regularization=lambda var: m_cost)
+                torch.autograd.backward([res["variance"], res["volume_mean"]], [m_gvar, m_gvol])
+                g = m_feat.grad
+                m_feat.grad = None
+                m_cost.grad = None
+                return g
+            g_a = det_step().clone()
+            g_b = det_step().clone()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                det_step()
+            torch.cuda.synchronize()
+            ms_det = (time.perf_counter() - t0) / 20 * 1e3
+            module_api["deterministic"] = {"value": 1e3 / ms_det, "unit": UNIT, "ms_per_scene": round(ms_det, 4),
+                                           "bit_identical_runs": bool(torch.equal(g_a, g_b)),
+                                           "what": "MVSDetHotPath(deterministic=True): backward accumulates in 64-bit "
+                                                   "fixed point with integer REDs (mvsd_*_bwd_det); opt-in"}
+            del hot_det, g_a, g_b
         del hot, m_feat, m_cost
 
     # ---- fp32-feature line (1e-4 parity is proven on fp32 features; their backward is the lean kernel)

@@ -136,6 +136,22 @@ int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout,
                          int V, int C, int D, int H, int W, int k, int ref_begin,
                          int n_feat_views, void* stream);
 
+/* Deterministic form of mvsd_plane_sweep_bwd (bit-reproducible gradients): the
+ * contributions are added as signed 64-bit fixed point with 32 fractional bits
+ * (integer REDs are order-independent; resolution 2.3e-10, |values| < 2^31) into
+ * g_feat_q (nhwc int64, extent of feat, caller zero-fills); mvsd_fixed_to_float
+ * converts the sums back (n elements, one rounding each).  Un-merged pixel-per-warp
+ * scatter with scalar 64-bit REDs: ~8x the time of mvsd_plane_sweep_bwd (a whole
+ * scene forward + backward: 7.3 ms instead of 1.2 ms).  Opt-in reproducibility mode;
+ * not the benchmarked path. */
+int mvsd_plane_sweep_bwd_det(const void* g_out, int g_dtype, int g_layout,
+                             const void* feat, int feat_dtype,
+                             const int32_t* nbr_ids, const float* hom,
+                             const float* depth_values, int64_t* g_feat_q,
+                             int V, int C, int D, int H, int W, int k, int ref_begin,
+                             int n_feat_views, void* stream);
+int mvsd_fixed_to_float(const int64_t* src, float* dst, int64_t n, void* stream);
+
 /* ---- f4: group-wise correlation cost volume over the same sweep ----------- *
  * The optional cost volume of SURVEY.md 8(f) rank 4; in the reference it is the
  * inline arithmetic of mvs_models/lss_fpn.py:485-506 (a branch no shipped config
@@ -267,6 +283,16 @@ int mvsd_backproject_bwd(const float* g_out, int g_layout, int mode,
                          int V, int C, int h, int w, int T, int N, void* stream);
 /* pn = prob / sum_T prob (mvsdet.py:1395-1396) backward: g_pn -> g_prob, all
  * three addressed with the dp_* strides; overwrites g_prob on the [h,w] crop. */
+/* Deterministic form of mvsd_backproject_bwd, MVSD_BP_MEAN only: g_feat_q / g_pn_q are
+ * 64-bit fixed-point accumulators (see mvsd_plane_sweep_bwd_det; g_pn_q has prob's
+ * strides and may be NULL); convert with mvsd_fixed_to_float before mvsd_prob_norm_bwd. */
+int mvsd_backproject_bwd_det(const float* g_out, int g_layout, const int32_t* count,
+                             const void* feat, int feat_dtype, int feat_h, int feat_w,
+                             const float* points, const float* projection,
+                             const float* depth, const float* prob,
+                             int64_t dp_sv, int64_t dp_sy, int64_t dp_sx, int64_t dp_st,
+                             float vs_z, int64_t* g_feat_q, int64_t* g_pn_q,
+                             int V, int C, int h, int w, int T, int N, void* stream);
 int mvsd_prob_norm_bwd(const float* prob, const float* g_pn, float* g_prob,
                        int64_t dp_sv, int64_t dp_sy, int64_t dp_sx, int64_t dp_st,
                        int V, int h, int w, int T, void* stream);

@@ -33,6 +33,7 @@ struct BpParams {
   float vs_z;
   float* out; int32_t* count; uint8_t* valid; float* weight;
   const float* g_out; const int32_t* count_in; float* g_feat; float* g_pn;
+  long long* g_feat_q; long long* g_pn_q;      // deterministic form: 64-bit fixed-point accumulators
   int V, C, h, w, T, N, feat_h, feat_w;
 };
 
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kBpWarps * 32) backproject_fwd_kernel(const Bp
 //   dL/dfeat[i,y,x,:] += weight * g_vol ;  dL/dweight = sum_c g_vol[c] * feat[c]
 //   dL/dpn[i,y,x,j*]  += dL/dweight  (j* = arg max routed by torch.max)
 // ---------------------------------------------------------------------------
-template <typename TIn, int G, int MODE, bool CFIRST, int kBpWarps>
+template <typename TIn, int G, int MODE, bool CFIRST, int kBpWarps, bool DET = false>
 __global__ void __launch_bounds__(kBpWarps * 32) backproject_bwd_kernel(const BpParams p) {
   __shared__ float s_tile[CFIRST ? kBpVox * kTileStride : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -240,12 +241,16 @@ __global__ void __launch_bounds__(kBpWarps * 32) backproject_bwd_kernel(const Bp
           const float4 f = Io<TIn>::ld(feat + fo + 128 * g);
           dot = fmaf(gg.x, f.x, dot); dot = fmaf(gg.y, f.y, dot);
           dot = fmaf(gg.z, f.z, dot); dot = fmaf(gg.w, f.w, dot);
-          red_add_f32x4(p.g_feat + fo + 128 * g,
-                        make_float4(gg.x * wgt, gg.y * wgt, gg.z * wgt, gg.w * wgt));
+          const float4 contrib = make_float4(gg.x * wgt, gg.y * wgt, gg.z * wgt, gg.w * wgt);
+          if (DET) red_add_fixed4(p.g_feat_q + fo + 128 * g, contrib);
+          else red_add_f32x4(p.g_feat + fo + 128 * g, contrib);
         }
         dot = warp_sum(dot);
-        if (lane == src && hit.jstar >= 0 && p.g_pn)
-          atomicAdd(p.g_pn + vs * p.sv + hit.y * p.sy + hit.x * p.sx + hit.jstar * p.st, dot);
+        if (lane == src && hit.jstar >= 0) {
+          const int64_t po = vs * p.sv + hit.y * p.sy + hit.x * p.sx + hit.jstar * p.st;
+          if (DET) { if (p.g_pn_q) red_add_fixed(p.g_pn_q + po, dot); }
+          else if (p.g_pn) atomicAdd(p.g_pn + po, dot);
+        }
       }
     }
   }
@@ -384,6 +389,48 @@ extern "C" int mvsd_backproject_bwd(const float* g_out, int g_layout, int mode,
   p.V = V; p.C = C; p.h = h; p.w = w; p.T = T; p.N = N; p.feat_h = feat_h; p.feat_w = feat_w;
   return launch_bp<true>(p, feat_dtype, mode, g_layout == MVSD_CHANNELS_FIRST,
                          static_cast<cudaStream_t>(stream));
+}
+
+// Deterministic form of the MEAN-mode backward: the same kernel with 64-bit fixed-point integer REDs
+// (common.cuh) into g_feat_q (nhwc, extent of feat) and g_pn_q (strides of prob).
+template <typename TIn, int G>
+static int launch_bp_bwd_det(const BpParams& p, bool cfirst, cudaStream_t st) {
+  dim3 grid((p.N + kBpVox - 1) / kBpVox);
+  if (cfirst) backproject_bwd_kernel<TIn, G, MVSD_BP_MEAN, true, 16, true><<<grid, 16 * 32, 0, st>>>(p);
+  else backproject_bwd_kernel<TIn, G, MVSD_BP_MEAN, false, 16, true><<<grid, 16 * 32, 0, st>>>(p);
+  count_launch();
+  return check_launch("backproject_bwd_det");
+}
+
+extern "C" int mvsd_backproject_bwd_det(const float* g_out, int g_layout, const int32_t* count,
+                                        const void* feat, int feat_dtype, int feat_h, int feat_w,
+                                        const float* points, const float* projection, const float* depth,
+                                        const float* prob, int64_t dp_sv, int64_t dp_sy, int64_t dp_sx,
+                                        int64_t dp_st, float vs_z, int64_t* g_feat_q, int64_t* g_pn_q, int V,
+                                        int C, int h, int w, int T, int N, void* stream) {
+  if (int e = check_bp("backproject_bwd_det", V, C, h, w, T, N, feat_h, feat_w, MVSD_BP_MEAN, g_layout)) return e;
+  if (!g_out || !feat || !points || !projection || !depth || !prob || !g_feat_q || !count)
+    return fail(MVSD_ERR_INVALID_ARG, "backproject_bwd_det: null pointer");
+  BpParams p{};
+  p.feat = feat; p.points = points; p.proj = projection; p.depth = depth; p.prob = prob;
+  p.sv = dp_sv; p.sy = dp_sy; p.sx = dp_sx; p.st = dp_st; p.vs_z = vs_z;
+  p.g_out = g_out; p.count_in = count;
+  p.g_feat_q = reinterpret_cast<long long*>(g_feat_q); p.g_pn_q = reinterpret_cast<long long*>(g_pn_q);
+  p.V = V; p.C = C; p.h = h; p.w = w; p.T = T; p.N = N; p.feat_h = feat_h; p.feat_w = feat_w;
+  const bool cfirst = g_layout == MVSD_CHANNELS_FIRST;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int G = (C + 127) / 128;
+  if (feat_dtype == MVSD_F32) {
+    if (G == 1) return launch_bp_bwd_det<float, 1>(p, cfirst, st);
+    if (G == 2) return launch_bp_bwd_det<float, 2>(p, cfirst, st);
+    return launch_bp_bwd_det<float, 4>(p, cfirst, st);
+  }
+  if (feat_dtype == MVSD_BF16) {
+    if (G == 1) return launch_bp_bwd_det<__nv_bfloat16, 1>(p, cfirst, st);
+    if (G == 2) return launch_bp_bwd_det<__nv_bfloat16, 2>(p, cfirst, st);
+    return launch_bp_bwd_det<__nv_bfloat16, 4>(p, cfirst, st);
+  }
+  return fail(MVSD_ERR_INVALID_ARG, "backproject_bwd_det: bad dtype");
 }
 
 extern "C" int mvsd_prob_norm_bwd(const float* prob, const float* g_pn, float* g_prob,

@@ -80,6 +80,22 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float4 v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Deterministic accumulation (the *_det entry points): fp32 REDs add in whatever order the warps
+// arrive, so a gradient is reproducible to ~3e-6 of its rms, not bit for bit.  Integer addition is
+// associative: every contribution is converted to signed 64-bit fixed point with 32 fractional bits
+// (x * 2^32 is exact in fp32, the conversion is exact for |x| < 2^31) and added with 64-bit integer
+// REDs; the sum is converted back once (mvsd_fixed_to_float).  Resolution 2.3e-10, range +-2^31.
+constexpr float kFixedScale = 4294967296.0f;
+__device__ __forceinline__ void red_add_fixed(long long* p, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * kFixedScale));
+}
+__device__ __forceinline__ void red_add_fixed4(long long* p, float4 v) {
+  red_add_fixed(p + 0, v.x);
+  red_add_fixed(p + 1, v.y);
+  red_add_fixed(p + 2, v.z);
+  red_add_fixed(p + 3, v.w);
+}
+
 // ---- plane-sweep sample geometry -------------------------------------------
 // One bilinear sample of the homography warp: element offsets (pixel index
 // y*W+x, clamped into the map) of the four taps and their weights (zero for

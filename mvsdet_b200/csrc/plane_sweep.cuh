@@ -45,6 +45,7 @@ struct SweepParams {
   void* out;               // fwd output [V,D,H,W,C]
   const void* g_out;       // bwd upstream gradient, same layout
   float* g_feat;           // bwd: nhwc fp32, accumulated with RED
+  long long* g_feat_q;     // bwd, deterministic form: nhwc 64-bit fixed point (common.cuh), integer REDs
   int V, C, D, H, W, k;
   int ref_begin;           // feat index of reference view 0 (view sharding)
   int n_feat;              // views held by feat: neighbour ids outside [0, n_feat) give no sample

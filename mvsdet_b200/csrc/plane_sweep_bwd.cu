@@ -9,18 +9,23 @@
 
 namespace mvsd {
 
-template <int G, bool FULL>
-__device__ __forceinline__ void red_tap(float* dst, unsigned off, const float4 (&gw)[G], float w,
+// TAcc = float: fp32 vector REDs; TAcc = long long: the deterministic fixed-point form (common.cuh)
+__device__ __forceinline__ void red_vec(float* a, float4 v) { red_add_f32x4(a, v); }
+__device__ __forceinline__ void red_vec(long long* a, float4 v) { red_add_fixed4(a, v); }
+
+template <int G, bool FULL, typename TAcc>
+__device__ __forceinline__ void red_tap(TAcc* dst, unsigned off, const float4 (&gw)[G], float w,
                                         int c0, int C) {
   if (w == 0.f) return;                         // clamped (outside) tap: contributes nothing
-  float* a = at(dst, off);
+  TAcc* a = at(dst, off);
 #pragma unroll
   for (int g = 0; g < G; ++g)
-    if (group_on<FULL>(c0, g, C)) red_add_f32x4(a + 128 * g, f4scale(gw[g], w));
+    if (group_on<FULL>(c0, g, C)) red_vec(a + 128 * g, f4scale(gw[g], w));
 }
 
-template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool WARP_ONLY>
+template <typename TIn, typename TG, int KMAX, int G, bool FULL, bool WARP_ONLY, typename TAcc = float>
 __global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepParams p) {
+  TAcc* const g_acc = sizeof(TAcc) == 8 ? reinterpret_cast<TAcc*>(p.g_feat_q) : reinterpret_cast<TAcc*>(p.g_feat);
   __shared__ WarpSample s_tab[kSweepWarps][kSlots];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const SweepCoord c = sweep_coord<G>(p, warp, lane);
@@ -40,13 +45,13 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepPar
     if (!WARP_ONLY && group_on<FULL>(c.c0, g, C)) ref[g] = Io<TIn>::ld(feat + ref_off + 128 * g);
   }
   const TIn* nsrc[KMAX];
-  float* ndst[KMAX];
+  TAcc* ndst[KMAX];
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) {
     int n = c.v + p.ref_begin;
     if (!WARP_ONLY && j < k) n = __ldg(p.nbr + (size_t)c.v * k + j);
     nsrc[j] = feat + (size_t)n * HW * C + c.c0;
-    ndst[j] = p.g_feat + (size_t)n * HW * C + c.c0;
+    ndst[j] = g_acc + (size_t)n * HW * C + c.c0;
   }
   const float inv_n = 1.0f / (float)(k + 1);
   const float two_inv_n = 2.0f * inv_n;
@@ -97,18 +102,18 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_bwd_kernel(const SweepPar
 #pragma unroll
         for (int g = 0; g < G; ++g)
           gw[g] = WARP_ONLY ? gv[g] : f4mul(gv[g], f4sub(wv[j][g], mu[g]));
-        red_tap<G, FULL>(ndst[j], s.p00, gw, s.w00, c.c0, C);
-        red_tap<G, FULL>(ndst[j], s.p01, gw, s.w01, c.c0, C);
-        red_tap<G, FULL>(ndst[j], s.p10, gw, s.w10, c.c0, C);
-        red_tap<G, FULL>(ndst[j], s.p11, gw, s.w11, c.c0, C);
+        red_tap<G, FULL, TAcc>(ndst[j], s.p00, gw, s.w00, c.c0, C);
+        red_tap<G, FULL, TAcc>(ndst[j], s.p01, gw, s.w01, c.c0, C);
+        red_tap<G, FULL, TAcc>(ndst[j], s.p10, gw, s.w10, c.c0, C);
+        red_tap<G, FULL, TAcc>(ndst[j], s.p11, gw, s.w11, c.c0, C);
       }
     }
   }
   if (!WARP_ONLY) {
-    float* dst = p.g_feat + ref_off;
+    TAcc* dst = g_acc + ref_off;
 #pragma unroll
     for (int g = 0; g < G; ++g)
-      if (group_on<FULL>(c.c0, g, C)) red_add_f32x4(dst + 128 * g, gref[g]);
+      if (group_on<FULL>(c.c0, g, C)) red_vec(dst + 128 * g, gref[g]);
   }
 }
 
@@ -130,7 +135,24 @@ static int launch_bwd_k(SweepParams& p, cudaStream_t st) {
   return check_launch("plane_sweep_bwd");
 }
 
+// deterministic form: the pixel-per-warp kernel with 64-bit fixed-point integer REDs
+template <typename TIn, typename TG>
+static int launch_bwd_det(SweepParams& p, cudaStream_t st) {
+  dim3 grid;
+  const int G = sweep_groups(p.C);
+  if (!sweep_grid(p, G, grid)) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_bwd_det: grid too large");
+  if (G == 2) sweep_bwd_kernel<TIn, TG, 4, 2, false, false, long long><<<grid, kSweepThreads, 0, st>>>(p);
+  else sweep_bwd_kernel<TIn, TG, 4, 1, false, false, long long><<<grid, kSweepThreads, 0, st>>>(p);
+  count_launch();
+  return check_launch("plane_sweep_bwd_det");
+}
+
 int launch_bwd_run(SweepParams& p, int feat_dtype, int g_dtype, cudaStream_t st);
+
+__global__ void fixed_to_float_kernel(const long long* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)((double)src[i] * (1.0 / 4294967296.0));      // one rounding, to nearest
+}
 
 }  // namespace mvsd
 
@@ -164,6 +186,39 @@ extern "C" int mvsd_plane_sweep_bwd(const void* g_out, int g_dtype, int g_layout
   if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_BF16)
     return launch_bwd_k<__nv_bfloat16, __nv_bfloat16, false>(p, st);
   return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_bwd: dtype combination not built");
+}
+
+extern "C" int mvsd_plane_sweep_bwd_det(const void* g_out, int g_dtype, int g_layout, const void* feat,
+                                        int feat_dtype, const int32_t* nbr_ids, const float* hom,
+                                        const float* depth_values, int64_t* g_feat_q, int V, int C, int D,
+                                        int H, int W, int k, int ref_begin, int n_feat_views,
+                                        void* stream) {
+  if (int e = sweep_check("plane_sweep_bwd_det", V, C, D, H, W, k, g_layout)) return e;
+  if (!g_out || !feat || !g_feat_q || !depth_values || (k > 0 && (!nbr_ids || !hom)))
+    return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_bwd_det: null pointer");
+  if (ref_begin < 0 || (long long)ref_begin + V > n_feat_views)
+    return fail(MVSD_ERR_INVALID_ARG, "plane_sweep_bwd_det: reference views [%d, %d) exceed the %d feature views",
+                ref_begin, ref_begin + V, n_feat_views);
+  SweepParams p{};
+  p.feat = feat; p.nbr = nbr_ids; p.hom = hom; p.depth = depth_values; p.g_out = g_out;
+  p.g_feat_q = reinterpret_cast<long long*>(g_feat_q);
+  p.V = V; p.C = C; p.D = D; p.H = H; p.W = W; p.k = k; p.ref_begin = ref_begin; p.n_feat = n_feat_views;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (feat_dtype == MVSD_F32 && g_dtype == MVSD_F32) return launch_bwd_det<float, float>(p, st);
+  if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_F32) return launch_bwd_det<__nv_bfloat16, float>(p, st);
+  if (feat_dtype == MVSD_BF16 && g_dtype == MVSD_BF16) return launch_bwd_det<__nv_bfloat16, __nv_bfloat16>(p, st);
+  return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_bwd_det: dtype combination not built");
+}
+
+extern "C" int mvsd_fixed_to_float(const int64_t* src, float* dst, int64_t n, void* stream) {
+  if (n <= 0) return fail(MVSD_ERR_INVALID_ARG, "fixed_to_float: non-positive size");
+  if (!src || !dst) return fail(MVSD_ERR_INVALID_ARG, "fixed_to_float: null pointer");
+  const long long blocks = (n + 255) / 256;
+  if (blocks > 2147483647LL) return fail(MVSD_ERR_UNSUPPORTED, "fixed_to_float: too many elements");
+  fixed_to_float_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(src), dst, (long long)n);
+  count_launch();
+  return check_launch("fixed_to_float");
 }
 
 extern "C" int mvsd_homo_warp_bwd(const void* g_out, int g_dtype, int g_layout, const float* hom,

@@ -112,23 +112,41 @@ class FeatureGradSink:
     scene.  Created by ``pack_features(x, dtype, sink=True)``; an implementation detail of
     ``MVSDetHotPath.forward``."""
 
-    def __init__(self, shape, device):
+    def __init__(self, shape, device, deterministic: bool = False):
         self.shape = tuple(shape)          # logical [V,C,H,W]
         self.device = device
+        self.deterministic = bool(deterministic)
         self.buf: Optional[torch.Tensor] = None
 
     def get(self) -> torch.Tensor:
         """the accumulator (logical [V,C,H,W], channels-last memory), zero-filled on first use.
         (Pre-filling it at forward time on a side stream was measured: the cross-stream
-        ``record_stream`` defeats the caching allocator's block reuse, 820 -> 692 scenes/s.)"""
+        ``record_stream`` defeats the caching allocator's block reuse, 820 -> 692 scenes/s.)
+        ``deterministic``: int64 fixed point (32 fractional bits) for the ``*_det`` kernels, whose
+        integer REDs make the sum independent of the order the warps arrive in."""
         if self.buf is None:
             v, c, h, w = self.shape
-            self.buf = _zeros_nhwc(v, c, h, w, torch.float32, self.device)
+            self.buf = _zeros_nhwc(v, c, h, w, torch.int64 if self.deterministic else torch.float32, self.device)
         return self.buf
 
     def take(self) -> Optional[torch.Tensor]:
+        """-> the fp32 accumulator (converted once from fixed point in the deterministic form)"""
         buf, self.buf = self.buf, None
+        if buf is not None and self.deterministic:
+            buf = fixed_to_float(buf)
         return buf
+
+
+def fixed_to_float(q: torch.Tensor) -> torch.Tensor:
+    """mvsd_fixed_to_float: an int64 fixed-point accumulator of the ``*_det`` kernels -> fp32, same
+    shape and memory layout."""
+    _need_cuda("accumulator", q)
+    if q.dtype != torch.int64:
+        raise ValueError("fixed_to_float takes an int64 accumulator")
+    out = torch.empty_like(q, dtype=torch.float32)
+    if q.numel():
+        _lib.call("mvsd_fixed_to_float", q.data_ptr(), out.data_ptr(), q.numel(), _stream())
+    return out
 
 
 class _PackFeaturesSink(torch.autograd.Function):
@@ -177,7 +195,8 @@ class _PackFeatures(torch.autograd.Function):
         return out, None
 
 
-def pack_features(x: torch.Tensor, dtype: torch.dtype = torch.float32, sink: bool = False):
+def pack_features(x: torch.Tensor, dtype: torch.dtype = torch.float32, sink: bool = False,
+                  deterministic: bool = False):
     """[V,C,H,W] features -> the same logical tensor in channels_last memory
     format and ``dtype`` (fp32 or bf16).  A tensor that already has that layout
     and dtype is returned as is; an fp32 NCHW-contiguous tensor (the reference's
@@ -195,7 +214,7 @@ def pack_features(x: torch.Tensor, dtype: torch.dtype = torch.float32, sink: boo
     if x.dtype != torch.float32 or not x.is_contiguous():
         x = x.float().contiguous()
     if sink and x.requires_grad and torch.is_grad_enabled():
-        gs = FeatureGradSink(x.shape, x.device)
+        gs = FeatureGradSink(x.shape, x.device, deterministic)
         return _PackFeaturesSink.apply(x, dtype, gs), gs
     out = _PackFeatures.apply(x, dtype)
     return (out, None) if sink else out
@@ -262,6 +281,11 @@ def _sweep_bwd_raw(g, feat, nbr_ids, hom, depth_values, ref_begin, acc=None):
     k = nbr_ids.shape[1]
     gdt = torch.bfloat16 if (g.dtype == torch.bfloat16 and feat.dtype == torch.bfloat16) else torch.float32
     g = _as_ndhwc(g, gdt)
+    if acc is not None and acc.dtype == torch.int64:        # deterministic sink: fixed-point integer REDs
+        _lib.call("mvsd_plane_sweep_bwd_det", g.data_ptr(), _code(g.dtype), CHANNELS_LAST,
+                  feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids), _ptr(hom),
+                  depth_values.data_ptr(), acc.data_ptr(), v, c, d, h, w, k, ref_begin, vf, _stream())
+        return None
     g_feat = acc if acc is not None else _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
     _lib.call("mvsd_plane_sweep_bwd", g.data_ptr(), _code(g.dtype), CHANNELS_LAST,
               feat.data_ptr(), _code(feat.dtype), _ptr(nbr_ids), _ptr(hom),
@@ -336,6 +360,8 @@ def _corr_bwd_raw(g, feat, nbr_ids, hom, depth_values, num_groups, ref_begin, ac
     v, k = nbr_ids.shape
     d = depth_values.shape[1]
     g = g.float().permute(0, 1, 3, 4, 5, 2).contiguous()          # no copy when it arrives in out's layout
+    if acc is not None and acc.dtype != torch.float32:
+        raise ValueError("the group-correlation backward has no deterministic form")
     g_feat = acc if acc is not None else _zeros_nhwc(vf, c, h, w, torch.float32, feat.device)
     _lib.call("mvsd_plane_sweep_groupcorr_bwd", g.data_ptr(), feat.data_ptr(), _code(feat.dtype),
               nbr_ids.data_ptr(), hom.data_ptr(), depth_values.data_ptr(), g_feat.data_ptr(),
@@ -663,6 +689,23 @@ def _bp_bwd_raw(g_out, feat, points, projection, est_depth, est_dens, count, vs_
     sv, st, sy, sx = est_depth.stride()
     g_out = g_out.float()
     g_mem = g_out.contiguous() if channels_first else g_out.t().contiguous()
+    if acc is not None and acc.dtype == torch.int64:        # deterministic sink (MEAN mode only)
+        if mode != BP_MEAN:
+            raise ValueError("the deterministic backward is built for the mean aggregation only")
+        g_pn_q = torch.zeros(est_dens.shape, dtype=torch.int64, device=feat.device)
+        g_prob = _zeros_strided_like(est_dens)
+        qs = g_pn_q.stride()                                 # contiguous [V,T,fh,fw]
+        if (qs[0], qs[2], qs[3], qs[1]) != (sv, sy, sx, st):
+            raise ValueError("the deterministic backward needs contiguous [V,T,H,W] hypotheses")
+        _lib.call("mvsd_backproject_bwd_det", g_mem.data_ptr(),
+                  CHANNELS_FIRST if channels_first else CHANNELS_LAST, count.data_ptr(),
+                  feat.data_ptr(), _code(feat.dtype), fh, fw, points.data_ptr(), projection.data_ptr(),
+                  est_depth.data_ptr(), est_dens.data_ptr(), sv, sy, sx, st, float(vs_z),
+                  acc.data_ptr(), g_pn_q.data_ptr(), v, c, h, w, t, n, _stream())
+        g_pn = fixed_to_float(g_pn_q)
+        _lib.call("mvsd_prob_norm_bwd", est_dens.data_ptr(), g_pn.data_ptr(), g_prob.data_ptr(),
+                  sv, sy, sx, st, v, h, w, t, _stream())
+        return None, g_prob
     g_feat = acc if acc is not None else _zeros_nhwc(v, c, fh, fw, torch.float32, feat.device)
     g_pn = _zeros_strided_like(est_dens)
     g_prob = _zeros_strided_like(est_dens)
