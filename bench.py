@@ -420,7 +420,11 @@ def run_sharded_leg(args, dev, rank, world, dist):
            "ms_whole_scene_1gpu_graph": None if ms_graph is None else round(ms_graph, 4),
            "bytes": int(whole["volume_mean"].numel() * 4 + whole["count"].numel() * 4)}
     pipe = sharded.ShardedScenePipeline(hot, cfg, dev)
-    pipe.load(scene["feature"], scene["cost_out"], scene["img_meta"])
+    pipe.load(scene["feature"], scene["cost_out"], scene["img_meta"])      # pose-clustered blocks
+    out["partition"] = ("pose-clustered blocks (sharded.pose_order)" if pipe.view_order != list(range(cfg.n_views))
+                        else "contiguous blocks")
+    out["halo_views_per_rank"] = pipe.halo_counts
+    out["halo_views_per_rank_contiguous"] = sharded.halo_counts(geo_full.neighbor_ids_ref(), world)
     results = {}
     for mode in ("p2p", "nccl"):
         try:
@@ -497,20 +501,24 @@ def run_sharded_train_leg(args, dev, rank, world, dist):
     torch.cuda.synchronize()
     g1 = p1.capture()
     ms_whole = timed(g1.replay)
-    begin, end = sharded.partition_views(cfg.n_views, world, rank)
+    pipe = sharded.ShardedScenePipeline(hot, cfg, dev)
+    pipe.load(scene["feature"], scene["cost_out"], scene["img_meta"])      # pose-clustered blocks
+    own = pipe.view_ids.to(dev)                                             # the views this rank owns
     ref_vol, ref_count = p1.volume_mean.clone(), p1.count.clone()
-    ref_g_feat, ref_g_cost = p1.g_feature[begin:end].clone(), p1.g_cost_out[begin:end].clone()
+    ref_g_feat, ref_g_cost = p1.g_feature[own].clone(), p1.g_cost_out[own].clone()
     g_scale = float(p1.g_feature.abs().max())
     del g1, p1
     torch.cuda.empty_cache()
-
-    pipe = sharded.ShardedScenePipeline(hot, cfg, dev)
-    pipe.load(scene["feature"], scene["cost_out"], scene["img_meta"])
     g_vol = scene["g_volume_mean"].to(dev)
-    g_var = scene["g_variance"][begin:end].to(dev).contiguous(memory_format=torch.channels_last_3d)
+    g_var = scene["g_variance"][pipe.view_ids].to(dev).contiguous(memory_format=torch.channels_last_3d)
     out = {"workload": f"BASELINE.json configs[3]: ARKitScenes-shaped scene (V={cfg.n_views}, per-view intrinsics, "
                        f"near/far {cfg.near_far_range}), forward + backward, reference views sharded over {world} GPUs",
-           "views": cfg.n_views, "ms_whole_scene_1gpu_graph": round(ms_whole, 4)}
+           "views": cfg.n_views, "ms_whole_scene_1gpu_graph": round(ms_whole, 4),
+           "partition": "pose-clustered blocks (sharded.pose_order)" if pipe.view_order != list(range(cfg.n_views))
+                        else "contiguous blocks",
+           "halo_views_per_rank": pipe.halo_counts,
+           "halo_views_per_rank_contiguous": sharded.halo_counts(
+               hot.geometry(scene["img_meta"], "cpu", prologue="host").neighbor_ids_host, world)}
     results = {}
     for mode in ("p2p", "nccl"):
         try:

@@ -65,7 +65,10 @@ __device__ __forceinline__ LaneHit lane_test(const BpParams& p, int vi, float X,
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <typename TIn, int G, int MODE, bool CFIRST, int kBpWarps>
+// PAIR (V <= 16, the view-sharded ranks): the projection + depth tests of the warp's TWO voxels run in one
+// pass, views of voxel 0 on lanes 0-15 and of voxel 1 on lanes 16-31 -- with few views per rank the kernel is
+// all test latency and half of the lanes were idle.  Same gather order (views ascending): same bits.
+template <typename TIn, int G, int MODE, bool CFIRST, int kBpWarps, bool PAIR = false>
 __global__ void __launch_bounds__(kBpWarps * 32) backproject_fwd_kernel(const BpParams p) {
   __shared__ float s_tile[CFIRST ? kBpVox * kTileStride : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -73,8 +76,68 @@ __global__ void __launch_bounds__(kBpWarps * 32) backproject_fwd_kernel(const Bp
   const TIn* feat = static_cast<const TIn*>(p.feat);
   const size_t map = (size_t)p.feat_h * p.feat_w;
   constexpr int VPW = kBpVox / kBpWarps;       // voxels per warp
+  static_assert(!PAIR || (VPW == 2 && MODE != MVSD_BP_PER_VIEW), "pair form: two voxels per warp, aggregated modes");
   float4 res[VPW][G];
 
+  if constexpr (PAIR) {
+    const int half = lane >> 4, vi = lane & 15;
+    const int ul = blockIdx.x * kBpVox + warp * VPW + half;          // this lane's voxel
+#pragma unroll
+    for (int i = 0; i < VPW; ++i)
+#pragma unroll
+      for (int g = 0; g < G; ++g) res[i][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    LaneHit hit;
+    hit.foff = 0; hit.x = 0; hit.y = 0; hit.jstar = -1; hit.weight = 0.f; hit.valid = false;
+    if (ul < N && vi < p.V) {
+      const float X = __ldg(p.points + ul), Y = __ldg(p.points + N + ul), Z = __ldg(p.points + 2 * (size_t)N + ul);
+      hit = lane_test(p, vi, X, Y, Z);
+      if (p.valid) p.valid[(size_t)vi * N + ul] = hit.valid ? 1 : 0;
+      if (p.weight) p.weight[(size_t)vi * N + ul] = hit.weight;
+    }
+    const unsigned both = __ballot_sync(0xffffffffu, hit.valid);
+#pragma unroll
+    for (int i = 0; i < VPW; ++i) {
+      const int u = blockIdx.x * kBpVox + warp * VPW + i;
+      unsigned mask = (both >> (16 * i)) & 0xffffu;
+      const int cnt = __popc(mask);
+      while (mask) {
+        const int vs = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int foff = __shfl_sync(0xffffffffu, hit.foff, vs + 16 * i);
+        const float wgt = __shfl_sync(0xffffffffu, hit.weight, vs + 16 * i);
+        const TIn* f = feat + ((size_t)vs * map + foff) * C + 4 * lane;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (128 * g + 4 * lane >= C) continue;
+          float4 a = Io<TIn>::ld(f + 128 * g);
+          a.x = __fmul_rn(a.x, wgt); a.y = __fmul_rn(a.y, wgt);
+          a.z = __fmul_rn(a.z, wgt); a.w = __fmul_rn(a.w, wgt);
+          res[i][g].x = __fadd_rn(res[i][g].x, a.x); res[i][g].y = __fadd_rn(res[i][g].y, a.y);
+          res[i][g].z = __fadd_rn(res[i][g].z, a.z); res[i][g].w = __fadd_rn(res[i][g].w, a.w);
+        }
+      }
+      if (u >= N) continue;
+      if (lane == 0 && p.count) p.count[u] = cnt;
+      if (MODE == MVSD_BP_MEAN) {
+        const float den = __fadd_rn((float)cnt, 1e-8f);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (cnt == 0) {
+            res[i][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+            res[i][g].x = __fdiv_rn(res[i][g].x, den); res[i][g].y = __fdiv_rn(res[i][g].y, den);
+            res[i][g].z = __fdiv_rn(res[i][g].z, den); res[i][g].w = __fdiv_rn(res[i][g].w, den);
+          }
+        }
+      }
+      if (!CFIRST) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (128 * g + 4 * lane < C)
+            Io<float>::st(p.out + (size_t)u * C + 128 * g + 4 * lane, res[i][g]);
+      }
+    }
+  } else {
 #pragma unroll
   for (int i = 0; i < VPW; ++i) {
     const int u = blockIdx.x * kBpVox + warp * VPW + i;
@@ -137,6 +200,7 @@ __global__ void __launch_bounds__(kBpWarps * 32) backproject_fwd_kernel(const Bp
             Io<float>::st(p.out + (size_t)u * C + 128 * g + 4 * lane, res[i][g]);
       }
     }
+  }
   }
 
   if (MODE != MVSD_BP_PER_VIEW && CFIRST) {
@@ -293,7 +357,10 @@ static int launch_bp_warps(const BpParams& p, int mode, bool cfirst, cudaStream_
 #define MVSD_BP_LAUNCH(M, CF)                                                                 \
   do {                                                                                        \
     if (BWD) backproject_bwd_kernel<TIn, G, M, CF, WARPS><<<grid, WARPS * 32, 0, st>>>(p);    \
-    else backproject_fwd_kernel<TIn, G, M, CF, WARPS><<<grid, WARPS * 32, 0, st>>>(p);        \
+    else if constexpr (M != MVSD_BP_PER_VIEW && kBpVox / WARPS == 2) {                        \
+      if (p.V <= 16) backproject_fwd_kernel<TIn, G, M, CF, WARPS, true><<<grid, WARPS * 32, 0, st>>>(p); \
+      else backproject_fwd_kernel<TIn, G, M, CF, WARPS><<<grid, WARPS * 32, 0, st>>>(p);      \
+    } else backproject_fwd_kernel<TIn, G, M, CF, WARPS><<<grid, WARPS * 32, 0, st>>>(p);      \
   } while (0)
   if (mode == MVSD_BP_PER_VIEW) MVSD_BP_LAUNCH(MVSD_BP_PER_VIEW, false);
   else if (mode == MVSD_BP_MEAN && cfirst) MVSD_BP_LAUNCH(MVSD_BP_MEAN, true);

@@ -89,7 +89,7 @@ def _worker_pipeline(rank, world, port, ret):
         torch.autograd.backward([whole["variance"], whole["volume_mean"]], [g_var, g_vol])
         pipe = sharded.ShardedScenePipeline(hot, cfg, dev)
         pipe.load(scene["feature"], scene["cost_out"], scene["img_meta"])
-        b, e = pipe.lg.begin, pipe.lg.end
+        own = pipe.view_ids.to(dev)                          # pose-clustered block: the views this rank owns
         ok = {}
         for mode in ("p2p", "nccl"):
             for _ in range(3):
@@ -102,11 +102,11 @@ def _worker_pipeline(rank, world, port, ret):
             ok[mode + "_stream_err"] = float((res["volume_mean"] - whole["volume_mean"]).abs().max())
         pipe.forward("p2p")
         for _ in range(2):                                   # twice: the accumulators are reused
-            g_feat, g_cost = pipe.backward(g_vol, g_var[b:e].contiguous(memory_format=torch.channels_last_3d))
+            g_feat, g_cost = pipe.backward(g_vol, g_var[own].contiguous(memory_format=torch.channels_last_3d))
         torch.cuda.synchronize()
-        ok["g_feat_err"] = float((g_feat - feat.grad[b:e]).abs().max())
+        ok["g_feat_err"] = float((g_feat - feat.grad[own]).abs().max())
         ok["g_feat_scale"] = float(feat.grad.abs().max())
-        ok["g_cost_err"] = float((g_cost - cost.grad[b:e]).abs().max())
+        ok["g_cost_err"] = float((g_cost - cost.grad[own]).abs().max())
         ok["scale"] = float(whole["volume_mean"].abs().max())
         pipe.close()
         ret[rank] = ok

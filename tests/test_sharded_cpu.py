@@ -16,6 +16,7 @@ import torch.multiprocessing as mp
 
 from helpers import load_golden, oracle_chain
 from mvsdet_b200 import sharded
+from mvsdet_b200.scene import SceneConfig, make_scene
 from oracle import mvsdet_oracle as O
 
 
@@ -213,3 +214,41 @@ def test_two_rank_gloo_halo_exchange(tmp_path):
     for r in range(world):
         z = np.load(tmp_path / f"halo{r}.npz")
         np.testing.assert_allclose(z["mine"], z["want"], rtol=0, atol=1e-12)
+
+
+def test_pose_order_is_a_permutation_that_never_adds_halos():
+    """sharded.pose_order: pose-clustered blocks.  On the multi-turn helix of the synthetic
+    scenes the pose neighbours sit one turn away, so contiguous index blocks need many halo maps."""
+    from mvsdet_b200 import geometry as G
+    for v, world in ((80, 8), (40, 8), (80, 4), (20, 2), (9, 2), (5, 8)):
+        cfg = SceneConfig(n_views=v)
+        scene = make_scene(cfg, seed=7, with_grads=False)
+        geo = G.scene_geometry(scene["img_meta"], stride=cfg.stride, near_far_range=cfg.near_far_range,
+                               num_depth=cfg.num_depth, n_voxels=cfg.n_voxels, voxel_size=cfg.voxel_size,
+                               device="cpu", prologue="host")
+        order = sharded.pose_order(scene["img_meta"]["lidar2img"]["extrinsic"], geo.neighbor_ids_host, world)
+        assert sorted(order) == list(range(v))
+        before = sharded.halo_counts(geo.neighbor_ids_host, world)
+        after = sharded.halo_counts(geo.neighbor_ids_host, world, order)
+        assert (max(after), sum(after)) <= (max(before), sum(before))
+        if v == 80 and world == 8:
+            assert max(before) >= 10 and max(after) <= 4, (before, after)      # 11-20 halo maps -> 1-3
+
+
+def test_permuted_scene_has_permuted_neighbours():
+    """kNN in pose space is permutation-equivariant: the ids computed from the re-ordered meta dict are the
+    re-numbered ids of the original scene (what ShardedScenePipeline.load relies on)."""
+    from mvsdet_b200 import geometry as G
+    cfg = SceneConfig(n_views=24, per_view_intrinsics=True)
+    scene = make_scene(cfg, seed=3, with_grads=False)
+    kw = dict(stride=cfg.stride, near_far_range=cfg.near_far_range, num_depth=cfg.num_depth,
+              n_voxels=cfg.n_voxels, voxel_size=cfg.voxel_size, device="cpu", prologue="host")
+    geo = G.scene_geometry(scene["img_meta"], **kw)
+    order = sharded.pose_order(scene["img_meta"]["lidar2img"]["extrinsic"], geo.neighbor_ids_host, 4)
+    meta_p = sharded.permute_img_meta(scene["img_meta"], order)
+    assert len(meta_p["lidar2img"]["intrinsic"]) == 24 and meta_p["img_shape"] == scene["img_meta"]["img_shape"]
+    geo_p = G.scene_geometry(meta_p, **kw)
+    inv = {g: i for i, g in enumerate(order)}
+    want = torch.tensor([[inv[int(x)] for x in geo.neighbor_ids_host[g].tolist()] for g in order])
+    assert torch.equal(geo_p.neighbor_ids_host, want)
+    assert torch.equal(geo_p.projection, geo.projection[order])
