@@ -90,11 +90,29 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_fwd_kernel(const SweepPar
 // issue as FMUL2 / FFMA2 / FADD2 -- the scalar kernel above is issue-bound
 // (profiles/r01_a_ncu_sweep_summary.txt: 81% issue-active, 314 instructions per
 // pixel-plane of which 160 are fp32 math).
+// CTA of the packed forward: a 2 x 2 pixel patch, 4 warps.  Measured on B200 (profiles/r02_bwd_experiments.md):
+// 4 x 2 (8 warps, the shape of the other pixel-per-warp kernels) 0.2606 ms, 2 x 2 and 4 x 1 0.2534, 2 x 1
+// 0.2626, 1 x 1 0.2759, 4 x 4 / 8 x 2 0.367 -- with 64 registers an SM holds 32 warps either way, smaller CTAs
+// drain and refill in finer steps, and below 4 warps the shared taps of neighbouring pixels stop meeting in L1.
+constexpr int kFwdPatchW = 2, kFwdPatchH = 2;
+constexpr int kFwdWarps = kFwdPatchW * kFwdPatchH, kFwdThreads = kFwdWarps * 32;
+
 template <typename TIn, typename TOut, int KMAX, int G, bool FULL>
-__global__ void __launch_bounds__(kSweepThreads) sweep_fwd_p_kernel(const SweepParams p) {
-  __shared__ WarpSample s_tab[kSweepWarps][kSlots];
+__global__ void __launch_bounds__(kFwdThreads) sweep_fwd_p_kernel(const SweepParams p) {
+  __shared__ WarpSample s_tab[kFwdWarps][kSlots];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const SweepCoord c = sweep_coord<G>(p, warp, lane);
+  SweepCoord c;
+  {
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; t /= p.tiles_y;
+    const int slice = t % p.slices;
+    c.v = t / p.slices;
+    c.x = tx * kFwdPatchW + (warp % kFwdPatchW);
+    c.y = ty * kFwdPatchH + (warp / kFwdPatchW);
+    c.ok = c.x < p.W && c.y < p.H;
+    c.c0 = slice * 128 * G + 4 * lane;
+  }
   if (!c.ok) return;
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
@@ -247,6 +265,13 @@ static int launch_fwd_k(SweepParams& p, cudaStream_t st) {
   dim3 grid;
   const int G = sweep_groups(p.C);
   if (!sweep_grid(p, G, grid)) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_fwd: grid too large");
+  if constexpr (!WARP_ONLY) {                 // the packed kernel has its own CTA patch
+    p.tiles_x = (p.W + kFwdPatchW - 1) / kFwdPatchW;
+    p.tiles_y = (p.H + kFwdPatchH - 1) / kFwdPatchH;
+    const long long blocks = (long long)p.V * p.slices * p.tiles_y * p.tiles_x;
+    if (blocks > 2147483647LL) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_fwd: grid too large");
+    grid = dim3((unsigned)blocks);
+  }
   const bool full = p.C % (128 * G) == 0;
   const int kmax = WARP_ONLY ? 1 : (p.k <= 1 ? 1 : (p.k == 2 ? 2 : 4));
 #define MVSD_FWD(KM, GG, FU)                                                           \
@@ -254,7 +279,7 @@ static int launch_fwd_k(SweepParams& p, cudaStream_t st) {
     if constexpr (WARP_ONLY)                                                           \
       sweep_fwd_kernel<TIn, TOut, KM, GG, FU, true><<<grid, kSweepThreads, 0, st>>>(p); \
     else                                                                               \
-      sweep_fwd_p_kernel<TIn, TOut, KM, GG, FU><<<grid, kSweepThreads, 0, st>>>(p);    \
+      sweep_fwd_p_kernel<TIn, TOut, KM, GG, FU><<<grid, kFwdThreads, 0, st>>>(p);      \
   } while (0)
 #define MVSD_FWD_G(KM)                                                            \
   do {                                                                            \
