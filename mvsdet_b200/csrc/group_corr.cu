@@ -40,12 +40,27 @@ __device__ __forceinline__ float lane_sum4(P4 v) {
 // KMAX = 2: exactly two neighbours (the reference's k, mvsdet.py:432), both neighbours' taps in flight
 // before the first blend (one L2 round trip per pixel-plane, like the forward sweep); KMAX = 4: any
 // k <= 4, one neighbour at a time.
+// CTA = 2 x 2 pixels, 4 warps, like the packed forward sweep (plane_sweep_fwd.cu: smaller CTAs measured faster)
+constexpr int kCorrPatchW = 2, kCorrPatchH = 2;
+constexpr int kCorrWarps = kCorrPatchW * kCorrPatchH, kCorrThreads = kCorrWarps * 32;
+
 template <typename TIn, int KMAX, int G, bool FULL>
-__global__ void __launch_bounds__(kSweepThreads, 4) corr_fwd_kernel(const CorrParams q) {
+__global__ void __launch_bounds__(kCorrThreads, 8) corr_fwd_kernel(const CorrParams q) {
   const SweepParams& p = q.s;
-  __shared__ WarpSample s_tab[kSweepWarps][kSlots];
+  __shared__ WarpSample s_tab[kCorrWarps][kSlots];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const SweepCoord c = sweep_coord<G>(p, warp, lane);
+  SweepCoord c;
+  {
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; t /= p.tiles_y;
+    const int slice = t % p.slices;
+    c.v = t / p.slices;
+    c.x = tx * kCorrPatchW + (warp % kCorrPatchW);
+    c.y = ty * kCorrPatchH + (warp / kCorrPatchW);
+    c.ok = c.x < p.W && c.y < p.H;
+    c.c0 = slice * 128 * G + 4 * lane;
+  }
   if (!c.ok) return;
   const int C = p.C, k = p.k, HW = p.H * p.W;
   const TIn* feat = static_cast<const TIn*>(p.feat);
@@ -234,12 +249,19 @@ static int corr_launch(CorrParams& q, cudaStream_t st) {
   dim3 grid;
   const int G = sweep_groups(q.s.C);
   if (!sweep_grid(q.s, G, grid)) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_groupcorr: grid too large");
+  if constexpr (!BWD) {                          // the forward has its own CTA patch
+    q.s.tiles_x = (q.s.W + kCorrPatchW - 1) / kCorrPatchW;
+    q.s.tiles_y = (q.s.H + kCorrPatchH - 1) / kCorrPatchH;
+    const long long blocks = (long long)q.s.V * q.s.slices * q.s.tiles_y * q.s.tiles_x;
+    if (blocks > 2147483647LL) return fail(MVSD_ERR_UNSUPPORTED, "plane_sweep_groupcorr: grid too large");
+    grid = dim3((unsigned)blocks);
+  }
   const bool full = q.s.C % (128 * G) == 0;
 #define MVSD_CORR(GG, FU)                                                        \
   do {                                                                           \
     if constexpr (BWD) corr_bwd_kernel<TIn, GG, FU><<<grid, kSweepThreads, 0, st>>>(q); \
-    else if (q.s.k == 2) corr_fwd_kernel<TIn, 2, GG, FU><<<grid, kSweepThreads, 0, st>>>(q); \
-    else corr_fwd_kernel<TIn, 4, GG, FU><<<grid, kSweepThreads, 0, st>>>(q);     \
+    else if (q.s.k == 2) corr_fwd_kernel<TIn, 2, GG, FU><<<grid, kCorrThreads, 0, st>>>(q); \
+    else corr_fwd_kernel<TIn, 4, GG, FU><<<grid, kCorrThreads, 0, st>>>(q);      \
   } while (0)
   if (G == 2) { if (full) MVSD_CORR(2, true); else MVSD_CORR(2, false); }
   else { if (full) MVSD_CORR(1, true); else MVSD_CORR(1, false); }
