@@ -98,7 +98,8 @@ constexpr int kFwdPatchW = 2, kFwdPatchH = 2;
 constexpr int kFwdWarps = kFwdPatchW * kFwdPatchH, kFwdThreads = kFwdWarps * 32;
 
 template <typename TIn, typename TOut, int KMAX, int G, bool FULL>
-__global__ void __launch_bounds__(kFwdThreads) sweep_fwd_p_kernel(const SweepParams p) {
+// 8 CTAs x 4 warps per SM = 64 registers (9 CTAs at 56 registers measured the same, 10 at 48 spill: 0.313 ms)
+__global__ void __launch_bounds__(kFwdThreads, 8) sweep_fwd_p_kernel(const SweepParams p) {
   __shared__ WarpSample s_tab[kFwdWarps][kSlots];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SweepCoord c;
