@@ -24,7 +24,8 @@
  * torch tensor of logical shape [V,C,H,W] in torch.channels_last memory
  * format.  Volumes with layout MVSD_CHANNELS_LAST are [V][D][H][W][C]
  * (torch.channels_last_3d of logical [V,C,D,H,W]).  C must be a multiple of 4
- * and at most 512.  Accumulation is always fp32.
+ * and at most 512.  Accumulation is always fp32 (64-bit fixed point in the
+ * bit-reproducible *_det forms of the two scatter backwards).
  */
 #ifndef MVSDET_B200_H_
 #define MVSDET_B200_H_
