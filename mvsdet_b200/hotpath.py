@@ -38,7 +38,7 @@ class MVSDetHotPath(nn.Module):
                  variance_dtype: torch.dtype = torch.float32,
                  channels_first_volume: bool = True, num_neighbors: int = 2,
                  dispatcher_ops: bool = False, strict_ncdhw_variance: bool = False,
-                 deterministic: bool = False):
+                 deterministic: bool = False, cost_volume: str = "variance", num_groups: int = 8):
         super().__init__()
         self.n_voxels = [int(n) for n in n_voxels]
         self.voxel_size = [float(s) for s in voxel_size]
@@ -64,6 +64,15 @@ class MVSDetHotPath(nn.Module):
         # backward takes 7.3 ms instead of 1.2 ms (un-merged scatter, scalar 64-bit REDs): a
         # reproducibility mode, not the fast path; the forward is deterministic either way.
         self.deterministic = bool(deterministic)
+        # "variance" (the reference, mvsdet.py:439-467) or "group_correlation": hand the cost-regularisation
+        # net the k group-wise correlation volumes [V,k,num_groups,D,H,W] instead (the
+        # arithmetic of mvs_models/lss_fpn.py:485-506) -- for a lighter net than CostRegNet_3DGS
+        if cost_volume not in ("variance", "group_correlation"):
+            raise ValueError("cost_volume must be 'variance' or 'group_correlation'")
+        self.cost_volume = cost_volume
+        self.num_groups = int(num_groups)
+        if cost_volume == "group_correlation" and deterministic:
+            raise ValueError("the group-correlation backward has no deterministic form")
         if self.deterministic and self.dispatcher_ops:
             raise ValueError("deterministic=True uses the shared gradient accumulator of the autograd.Function "
                              "layer; it is not available with dispatcher_ops=True")
@@ -120,7 +129,9 @@ class MVSDetHotPath(nn.Module):
         already channels_last / bf16).  Returns a dict with
           volume_mean [C,nx,ny,nz], valid [1,nx,ny,nz] (float count, as
           extract_feat returns it, mvsdet.py:698), count int32 [N],
-          variance, prob_volume, off_pred, est_depth, est_densities, est_idx, opacity,
+          variance (the cost volume handed to the net: the variance, or with
+          ``cost_volume="group_correlation"`` the [V,k,G,D,Hf,Wf] correlation volumes),
+          prob_volume, off_pred, est_depth, est_densities, est_idx, opacity,
           depth_coding [V,1,h,w] -- the reference's intermediates; ``nvs=True`` adds
           depth_scale [V,h*w,1], est_ray_depth [V,h*w,1,T] and ray_depth_coding [V,h*w,1]
           in the reference's layouts (mvsdet.py:488-494, :583), from the top-k kernel."""
@@ -133,9 +144,18 @@ class MVSDetHotPath(nn.Module):
         feat_cl, sink = ops.pack_features(feature, self.feature_dtype, sink=True, deterministic=self.deterministic)
         if self.dispatcher_ops:
             sink = None
-        variance = self.variance(feat_cl, geo, grad_sink=sink)
-        if self.strict_ncdhw_variance:
-            variance = ops.volume_to_ncdhw(variance)
+        if self.cost_volume == "group_correlation":
+            if self.dispatcher_ops:
+                from . import library
+                variance = library.plane_sweep_group_correlation(feat_cl, geo.neighbor_ids, geo.hom,
+                                                                 geo.depth_values, self.num_groups, 0)
+            else:
+                variance = ops.plane_sweep_group_correlation(feat_cl, geo.neighbor_ids, geo.hom, geo.depth_values,
+                                                             self.num_groups, grad_sink=sink)
+        else:
+            variance = self.variance(feat_cl, geo, grad_sink=sink)
+            if self.strict_ncdhw_variance:
+                variance = ops.volume_to_ncdhw(variance)
         cost_out = cost_net(variance)
         hyp = self.hypotheses(cost_out, geo.k_feat if nvs else None)
         prob, off, est_depth, est_dens, est_idx, coding = hyp[:6]

@@ -119,3 +119,63 @@ def test_group_correlation_dispatcher_op_matches_autograd_function():
     torch.library.opcheck(torch.ops.mvsdet_b200.plane_sweep_group_correlation.default,
                           (base, geo.neighbor_ids, geo.hom, geo.depth_values, 8, 0),
                           test_utils=("test_schema", "test_faketensor"))
+
+
+def test_hot_path_with_group_correlation_cost_volume():
+    """MVSDetHotPath(cost_volume="group_correlation"): a small cost net on the correlation volumes instead of
+    CostRegNet_3DGS on the variance; whole chain forward + backward against the oracle with the same net."""
+    from mvsdet_b200.hotpath import MVSDetHotPath
+    cfg = tiny_config(n_views=5, channels=32, num_depth=8)
+    scene = make_scene(cfg, 13)
+    groups = 8
+    torch.manual_seed(0)
+    net = torch.nn.Conv3d(2 * groups, 2, 3, padding=1)                      # [V, k*G, D, H, W] -> [V, 2, D, H, W]
+    hf, wf = cfg.feat_hw
+
+    def cost_net_for(mod):
+        # the plane ramp breaks the EXACT ties a zero-padded conv produces where no neighbour has a sample
+        # (torch.topk and the kernel order exact ties differently: documented deviation)
+        def run(vol):
+            ramp = torch.arange(cfg.num_depth, dtype=torch.float32, device=vol.device).view(1, 1, -1, 1, 1)
+            return mod(vol.reshape(vol.shape[0], 2 * groups, cfg.num_depth, hf, wf)) * 3.0 + 0.01 * ramp
+        return run
+
+    # oracle: the correlation volumes through the same net, then the reference chain from the cost volume on
+    f_ref = scene["feature"].clone().requires_grad_(True)
+    corr = O.scene_group_correlation(f_ref, scene["img_meta"], near_far_range=cfg.near_far_range,
+                                     num_depth=cfg.num_depth, num_groups=groups, stride=cfg.stride)
+    want_cost = cost_net_for(net)(corr)
+    want = O.hot_path(f_ref, scene["img_meta"], lambda var: want_cost, near_far_range=cfg.near_far_range,
+                      num_depth=cfg.num_depth, topk=cfg.topk, n_voxels=cfg.n_voxels, voxel_size=cfg.voxel_size,
+                      stride=cfg.stride)
+    g_vol = scene["g_volume_mean"]
+    want_g, = torch.autograd.grad(want["volume_mean"], f_ref, g_vol)
+    # CUDA
+    dev = torch.device("cuda")
+    net_d = torch.nn.Conv3d(2 * groups, 2, 3, padding=1).to(dev)
+    net_d.load_state_dict(net.state_dict())
+    mod = MVSDetHotPath(cfg.n_voxels, cfg.voxel_size, cfg.near_far_range, cfg.num_depth, cfg.topk,
+                        stride=cfg.stride, cost_volume="group_correlation", num_groups=groups)
+    f_dev = scene["feature"].to(dev).requires_grad_(True)
+    want_cost_d = want_cost.detach().to(dev)
+    seen = {}
+
+    def cost_net_cuda(vol):
+        # cuDNN's conv differs from the CPU's by ~1e-6, enough to flip a near-tied third hypothesis: the
+        # VALUES handed on are the oracle's (a + (b - a) == b exactly for a ~ b), the GRADIENT flows through
+        # the CUDA net -- the test is about the hand-off, not about cuDNN
+        cost = cost_net_for(net_d)(vol)
+        seen["cost_err"] = float((cost.detach() - want_cost_d).abs().max())
+        return cost + (want_cost_d - cost).detach()
+
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        res = mod(f_dev, scene["img_meta"], cost_regularization=cost_net_cuda)
+        got_g, = torch.autograd.grad(res["volume_mean"], f_dev, g_vol.to(dev))
+    torch.cuda.synchronize()
+    assert tuple(res["variance"].shape) == tuple(corr.shape)
+    _close(res["variance"], corr, "correlation volumes")
+    assert seen["cost_err"] <= 1e-4 * float(want_cost_d.abs().max()), seen
+    assert torch.equal(res["est_idx"].cpu(), want["est_idx"]), "top-k indices"
+    assert torch.equal(res["count"].cpu().reshape(-1), want["count"].reshape(-1).to(torch.int32))
+    _close(res["volume_mean"], want["volume_mean"], "volume_mean")
+    _close(got_g, want_g, "dL/dfeature through voxels and correlation volumes", rtol=1e-3, atol_scale=1e-3)
